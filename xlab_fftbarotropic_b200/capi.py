@@ -1,0 +1,188 @@
+"""ctypes binding of the C ABI (include/xfb.h) -- the same calls a cgo/JNI/C++ host would make.
+
+The product path has no CPU fallback: if libxfb.so is missing this module raises, and if no CUDA
+device is present xfb_create fails with XFB_E_CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libxfb.so")
+
+VORT, PSI, U, V, SRC, TFIL, DEFORM, DVORTDX, DVORTDY = range(9)
+TAB_GRADX, TAB_GRADY, TAB_LAP, TAB_LAPINV, TAB_MASK = range(5)
+
+SYMBOLS = [
+    "xfb_last_error", "xfb_create", "xfb_destroy", "xfb_sync", "xfb_gradx", "xfb_grady", "xfb_laplacian",
+    "xfb_invert_laplacian", "xfb_dealias", "xfb_get_table", "xfb_r2c", "xfb_c2r", "xfb_set_vorticity",
+    "xfb_set_spectrum", "xfb_get_spectrum", "xfb_set_source", "xfb_step", "xfb_get_field", "xfb_get_keff_hist",
+    "xfb_invert_pres", "xfb_launch_count", "xfb_stream", "xfb_size_supported",
+]
+
+_lib = None
+
+
+class XfbError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise XfbError(f"{LIB_PATH} is missing: build it with `python -m xlab_fftbarotropic_b200.build` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    L.xfb_last_error.restype = C.c_char_p
+    L.xfb_create.argtypes = [C.POINTER(vp), ci, ci, cf, cf, cf, ci, ci]
+    L.xfb_destroy.argtypes = [vp]
+    L.xfb_sync.argtypes = [vp]
+    for n in ("xfb_gradx", "xfb_grady", "xfb_laplacian", "xfb_invert_laplacian", "xfb_dealias", "xfb_r2c", "xfb_c2r"):
+        getattr(L, n).argtypes = [vp, vp, vp]
+    L.xfb_get_table.argtypes = [vp, ci, vp]
+    L.xfb_set_vorticity.argtypes = [vp, ci, vp]
+    L.xfb_set_spectrum.argtypes = [vp, ci, vp]
+    L.xfb_get_spectrum.argtypes = [vp, ci, vp]
+    L.xfb_set_source.argtypes = [vp, ci, vp]
+    L.xfb_step.argtypes = [vp, ci, cf]
+    L.xfb_get_field.argtypes = [vp, ci, ci, vp]
+    L.xfb_get_keff_hist.argtypes = [vp, ci, ci, cf, cf, vp, vp]
+    L.xfb_invert_pres.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, cf, cf]
+    L.xfb_launch_count.restype = C.c_longlong
+    L.xfb_launch_count.argtypes = [vp]
+    L.xfb_stream.restype = vp
+    L.xfb_stream.argtypes = [vp]
+    L.xfb_size_supported.argtypes = [ci, ci]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    """host numpy array or raw device address (int) -> void*"""
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Backend:
+    """Mirror of the reference operator class `fftwf_operation<XPTS,YPTS>` (src/fftwfop.hpp:9-29) plus the
+    2-D transforms and the RK4 driver of src/main.cpp, on one B200.  Arrays are numpy, reference layout."""
+
+    def __init__(self, nx: int, ny: int | None = None, lx: float = 600000.0, ly: float | None = None,
+                 nu: float = 6.5, batch: int = 1, device: int = 0):
+        ny = nx if ny is None else ny
+        ly = lx if ly is None else ly
+        self.nx, self.ny, self.hy, self.batch = nx, ny, ny // 2 + 1, batch
+        self.lx, self.ly, self.nu = lx, ly, nu
+        self._L = load()
+        self._h = C.c_void_p()
+        self._ck(self._L.xfb_create(C.byref(self._h), nx, ny, lx, ly, nu, batch, device))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise XfbError(f"xfb error {rc}: {self._L.xfb_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.xfb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- operator tier ---------------------------------------------------------------------------
+    def _spec(self, a):
+        return np.ascontiguousarray(a, dtype=np.complex64).reshape(self.nx, self.hy)
+
+    def _op(self, name, a):
+        a = self._spec(a)
+        out = np.empty_like(a)
+        self._ck(getattr(self._L, name)(self._h, _ptr(a), _ptr(out)))
+        return out
+
+    def gradx(self, a): return self._op("xfb_gradx", a)
+    def grady(self, a): return self._op("xfb_grady", a)
+    def laplacian(self, a): return self._op("xfb_laplacian", a)
+    def invertLaplacian(self, a): return self._op("xfb_invert_laplacian", a)
+    def dealiase(self, a): return self._op("xfb_dealias", a)
+
+    def table(self, which):
+        shape = {0: (self.nx,), 1: (self.hy,)}.get(which, (self.nx, self.hy))
+        out = np.empty(shape, np.float32)
+        self._ck(self._L.xfb_get_table(self._h, which, _ptr(out)))
+        return out
+
+    def r2c(self, f):
+        f = np.ascontiguousarray(f, dtype=np.float32).reshape(self.nx, self.ny)
+        out = np.empty((self.nx, self.hy), np.complex64)
+        self._ck(self._L.xfb_r2c(self._h, _ptr(f), _ptr(out)))
+        return out
+
+    def c2r(self, a):
+        a = self._spec(a)
+        out = np.empty((self.nx, self.ny), np.float32)
+        self._ck(self._L.xfb_c2r(self._h, _ptr(a), _ptr(out)))
+        return out
+
+    # -- stepper tier ----------------------------------------------------------------------------
+    def set_vorticity(self, f, member=0):
+        if not isinstance(f, (int, np.integer)):
+            f = np.ascontiguousarray(f, dtype=np.float32).reshape(self.nx, self.ny)
+        self._ck(self._L.xfb_set_vorticity(self._h, member, _ptr(f)))
+
+    def set_spectrum(self, z, member=0):
+        z = self._spec(z)
+        self._ck(self._L.xfb_set_spectrum(self._h, member, _ptr(z)))
+
+    def get_spectrum(self, member=0):
+        out = np.empty((self.nx, self.hy), np.complex64)
+        self._ck(self._L.xfb_get_spectrum(self._h, member, _ptr(out)))
+        return out
+
+    def set_source(self, s, member=0):
+        if s is None:
+            self._ck(self._L.xfb_set_source(self._h, member, None))
+        else:
+            s = np.ascontiguousarray(s, dtype=np.float32).reshape(self.nx, self.ny)
+            self._ck(self._L.xfb_set_source(self._h, member, _ptr(s)))
+
+    def step(self, nsteps, dt):
+        self._ck(self._L.xfb_step(self._h, int(nsteps), float(dt)))
+
+    def sync(self):
+        self._ck(self._L.xfb_sync(self._h))
+
+    def get_field(self, which, member=0, out=None):
+        if out is None:
+            out = np.empty((self.nx, self.ny), np.float32)
+        self._ck(self._L.xfb_get_field(self._h, member, which, _ptr(out)))
+        return out
+
+    def keff_hist(self, nbins, cmin, cmax, member=0):
+        area = np.zeros(nbins, np.float64)
+        g2 = np.zeros(nbins, np.float64)
+        self._ck(self._L.xfb_get_keff_hist(self._h, member, nbins, cmin, cmax, _ptr(area), _ptr(g2)))
+        return area, g2
+
+    def invert_pres(self, psi, ref_x=0, ref_y=0, rho=1.0, f=1e-5):
+        psi = np.ascontiguousarray(psi, dtype=np.float32).reshape(self.nx, self.ny)
+        out = np.empty((self.nx, self.ny), np.float32)
+        self._ck(self._L.xfb_invert_pres(self._h, _ptr(psi), _ptr(out), ref_x, ref_y, rho, f))
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self._L.xfb_launch_count(self._h))
+
+    @property
+    def stream(self):
+        return self._L.xfb_stream(self._h)

@@ -1,0 +1,700 @@
+// xfb_api.cu -- the C ABI declared in include/xfb.h: handle, tables, operator tier, stepper.
+// No CPU fallback lives here: every entry point needs a CUDA device and says so when it fails.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/xfb.h"
+#include "xfb_internal.h"
+
+using namespace xfb;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *xfb_last_error(void) { return g_err; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) return fail(XFB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define CKL(h, call)                                                                                       \
+    do {                                                                                                   \
+        int e__ = (call);                                                                                  \
+        if (e__ != 0) return fail(XFB_E_CUDA, "%s: %s", #call, cudaGetErrorString((cudaError_t)e__));      \
+        (h)->launches++;                                                                                   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct xfb_handle_s {
+    int nx, ny, hy, pitch, batch, device;
+    float lx, ly, nu;
+    size_t grids, hgrids, hpad;   // per member: nx*ny, nx*(ny/2+1), nx*pitch
+    cudaStream_t stream;
+    // tables
+    cpx *tw;
+    int twn;
+    float *kx, *ky;
+    double *kx2, *ky2;
+    double mask_kd;
+    // stepper state (padded layout [batch][nx][pitch])
+    cpx *z0, *zk, *acc, *jint, *t[4];
+    float *src;          // [batch][nx][ny], allocated on first use
+    bool has_src;
+    bool have_state;     // a vorticity/spectrum has been set
+    bool tf_valid;       // t[0..3] hold the prologue of the current z0
+    // scratch for the operator tier / record path (one member)
+    float *real_a, *real_b, *real_c;
+    cpx *spec_a, *spec_b;      // padded layout
+    float *ref_a, *ref_b;      // reference layout half spectra (2*hgrids floats)
+    long long launches;
+};
+
+static int dev_alloc(void **p, size_t bytes)
+{
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return fail(XFB_E_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return 0;
+}
+
+static bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+extern "C" int xfb_size_supported(int nx, int ny)
+{
+    if (col_tile_width(nx) > 0 && row_size_ok(ny)) return 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pointwise kernels (operator tier, layout conversion, physical-space helpers)
+// ------------------------------------------------------------------------------------------------
+enum { OP_GRADX = 0, OP_GRADY = 1, OP_LAP = 2, OP_INVLAP = 3, OP_DEALIAS = 4, OP_COPY = 5 };
+
+struct PwParams {
+    const cpx *in;
+    cpx *out;
+    int nx, in_pitch, out_pitch, ncols;   // ncols columns are processed; the rest of out's pitch is zeroed
+    const float *kx, *ky;
+    const double *kx2, *ky2;
+    double mask_kd;
+    int op;
+};
+
+// One thread per spectral element.  Same float expressions as fftwfop.cpp:87-124.
+__global__ void pointwise_kernel(const PwParams p)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)p.nx * p.out_pitch;
+    if (idx >= total) return;
+    const int i = (int)(idx / p.out_pitch), j = (int)(idx % p.out_pitch);
+    if (j >= p.ncols) { p.out[idx] = mk(0.f, 0.f); return; }
+    const cpx z = p.in[(size_t)i * p.in_pitch + j];
+    cpx r = z;
+    switch (p.op) {
+    case OP_GRADX: { const float k = p.kx[i]; r = mk(__fmul_rn(-z.y, k), __fmul_rn(z.x, k)); break; }
+    case OP_GRADY: { const float k = p.ky[j]; r = mk(__fmul_rn(-z.y, k), __fmul_rn(z.x, k)); break; }
+    case OP_LAP: { const float l = lap_coe(p.kx2[i], p.ky2[j]); r = mk(__fmul_rn(z.x, l), __fmul_rn(z.y, l)); break; }
+    case OP_INVLAP: {
+        const float l = (i == 0 && j == 0) ? 1.0f : lap_coe(p.kx2[i], p.ky2[j]);
+        r = mk(__fdiv_rn(z.x, l), __fdiv_rn(z.y, l));
+        break;
+    }
+    case OP_DEALIAS: {
+        const long long ii = (i <= p.nx / 2) ? i : p.nx - i;
+        const float m = ((double)(ii * ii + (long long)j * j) >= p.mask_kd) ? 0.0f : 1.0f;
+        r = mk(__fmul_rn(z.x, m), __fmul_rn(z.y, m));
+        break;
+    }
+    default: break;
+    }
+    p.out[idx] = r;
+}
+
+// tables in the reference's H-sized form, for xfb_get_table (parity tests of fftwfop.cpp:40-68)
+__global__ void table_kernel(float *out, int which, int nx, int hy, const double *kx2, const double *ky2, double kd)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nx * hy) return;
+    const int i = (int)(idx / hy), j = (int)(idx % hy);
+    if (which == XFB_TAB_MASK) {
+        const long long ii = (i <= nx / 2) ? i : nx - i;
+        out[idx] = ((double)(ii * ii + (long long)j * j) >= kd) ? 0.0f : 1.0f;
+    } else {
+        const float l = lap_coe(kx2[i], ky2[j]);
+        out[idx] = (which == XFB_TAB_LAPINV && i == 0 && j == 0) ? 1.0f : l;
+    }
+}
+
+static int launch_pw(xfb_handle h, int op, const cpx *in, int in_pitch, cpx *out, int out_pitch, int ncols)
+{
+    PwParams p;
+    p.in = in; p.out = out; p.nx = h->nx; p.in_pitch = in_pitch; p.out_pitch = out_pitch; p.ncols = ncols;
+    p.kx = h->kx; p.ky = h->ky; p.kx2 = h->kx2; p.ky2 = h->ky2; p.mask_kd = h->mask_kd; p.op = op;
+    const long long total = (long long)h->nx * out_pitch;
+    const int threads = 256;
+    pointwise_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, h->stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(XFB_E_CUDA, "pointwise_kernel: %s", cudaGetErrorString(e));
+    h->launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------------
+extern "C" int xfb_create(xfb_handle *out, int nx, int ny, float lx, float ly, float nu, int batch, int device)
+{
+    if (!out) return fail(XFB_E_ARG, "xfb_create: null handle pointer");
+    *out = nullptr;
+    if (batch < 1) return fail(XFB_E_ARG, "xfb_create: batch must be >= 1");
+    if (!xfb_size_supported(nx, ny))
+        return fail(XFB_E_SIZE, "xfb_create: grid %dx%d not supported (powers of two 256..16384)", nx, ny);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(XFB_E_CUDA, "xfb_create: no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(XFB_E_ARG, "xfb_create: device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+
+    xfb_handle h = new (std::nothrow) xfb_handle_s();
+    if (!h) return fail(XFB_E_ARG, "xfb_create: out of host memory");
+    memset(h, 0, sizeof(*h));
+    h->nx = nx; h->ny = ny; h->hy = ny / 2 + 1; h->pitch = ny / 2 + 4; h->batch = batch; h->device = device;
+    h->lx = lx; h->ly = ly; h->nu = nu;
+    h->grids = (size_t)nx * ny; h->hgrids = (size_t)nx * h->hy; h->hpad = (size_t)nx * h->pitch;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+    // master twiddle table exp(-2 pi i k / twn), float64 -> float32 once
+    h->twn = nx > ny ? nx : ny;
+    {
+        std::vector<float2> tw(h->twn);
+        for (int k = 0; k < h->twn; ++k) {
+            const double a = -2.0 * M_PI * (double)k / (double)h->twn;
+            tw[k] = make_float2((float)cos(a), (float)sin(a));
+        }
+        if (dev_alloc((void **)&h->tw, sizeof(float2) * h->twn)) return XFB_E_CUDA;
+        CK(cudaMemcpy(h->tw, tw.data(), sizeof(float2) * h->twn, cudaMemcpyHostToDevice));
+    }
+    // wavenumber tables with the reference's float expressions (fftwfop.cpp:15-24, fftwfop.hpp:7)
+    {
+        const float TWOPI = acosf(-1.0f) * 2.0f;
+        std::vector<float> kx(nx), ky(h->pitch);
+        std::vector<double> kx2(nx), ky2(h->pitch);
+        for (int i = 0; i <= nx / 2; ++i) kx[i] = TWOPI * ((float)i) / lx;
+        for (int i = nx / 2 + 1; i < nx; ++i) kx[i] = -kx[nx - i];
+        for (int j = 0; j < h->pitch; ++j) ky[j] = TWOPI * ((float)j) / ly;
+        for (int i = 0; i < nx; ++i) kx2[i] = (double)kx[i] * (double)kx[i];
+        for (int j = 0; j < h->pitch; ++j) ky2[j] = (double)ky[j] * (double)ky[j];
+        if (dev_alloc((void **)&h->kx, sizeof(float) * nx) || dev_alloc((void **)&h->ky, sizeof(float) * h->pitch) ||
+            dev_alloc((void **)&h->kx2, sizeof(double) * nx) || dev_alloc((void **)&h->ky2, sizeof(double) * h->pitch))
+            return XFB_E_CUDA;
+        CK(cudaMemcpy(h->kx, kx.data(), sizeof(float) * nx, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->ky, ky.data(), sizeof(float) * h->pitch, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->kx2, kx2.data(), sizeof(double) * nx, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->ky2, ky2.data(), sizeof(double) * h->pitch, cudaMemcpyHostToDevice));
+        // fftwfop.cpp:11-12,57: ceil(((float)N)/3.0) squared and summed in double, stored as float
+        const int dkx = (int)ceil(((float)nx) / 3.0), dky = (int)ceil(((float)ny) / 3.0);
+        h->mask_kd = (double)(float)((double)dkx * dkx + (double)dky * dky);
+    }
+    const size_t sb = sizeof(cpx) * h->hpad * batch;
+    cpx **state[] = {&h->z0, &h->zk, &h->acc, &h->jint, &h->t[0], &h->t[1], &h->t[2], &h->t[3]};
+    for (auto pp : state) {
+        if (dev_alloc((void **)pp, sb)) return XFB_E_CUDA;
+        CK(cudaMemsetAsync(*pp, 0, sb, h->stream));
+    }
+    if (dev_alloc((void **)&h->real_a, sizeof(float) * h->grids) || dev_alloc((void **)&h->real_b, sizeof(float) * h->grids) ||
+        dev_alloc((void **)&h->real_c, sizeof(float) * h->grids) ||
+        dev_alloc((void **)&h->spec_a, sizeof(cpx) * h->hpad) || dev_alloc((void **)&h->spec_b, sizeof(cpx) * h->hpad) ||
+        dev_alloc((void **)&h->ref_a, sizeof(cpx) * h->hgrids) || dev_alloc((void **)&h->ref_b, sizeof(cpx) * h->hgrids))
+        return XFB_E_CUDA;
+    CK(cudaMemsetAsync(h->spec_a, 0, sizeof(cpx) * h->hpad, h->stream));
+    CK(cudaMemsetAsync(h->spec_b, 0, sizeof(cpx) * h->hpad, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return 0;
+}
+
+extern "C" int xfb_destroy(xfb_handle h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    void *ptrs[] = {h->tw, h->kx, h->ky, h->kx2, h->ky2, h->z0, h->zk, h->acc, h->jint, h->t[0], h->t[1], h->t[2],
+                    h->t[3], h->src, h->real_a, h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int xfb_sync(xfb_handle h)
+{
+    if (!h) return fail(XFB_E_ARG, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" long long xfb_launch_count(xfb_handle h) { return h ? h->launches : 0; }
+extern "C" void *xfb_stream(xfb_handle h) { return h ? (void *)h->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------------
+// staging helpers: bring a caller buffer to the device / back
+// ------------------------------------------------------------------------------------------------
+static int stage_in(xfb_handle h, const void *user, void *dev_scratch, size_t bytes, const void **dev)
+{
+    if (is_device_ptr(user)) { *dev = user; return 0; }
+    CK(cudaMemcpyAsync(dev_scratch, user, bytes, cudaMemcpyHostToDevice, h->stream));
+    *dev = dev_scratch;
+    return 0;
+}
+
+// returns the device buffer the result should be produced in
+static void *stage_out_target(const void *user, void *dev_scratch) { return is_device_ptr(user) ? (void *)user : dev_scratch; }
+
+static int stage_out(xfb_handle h, void *user, const void *dev, size_t bytes)
+{
+    if ((const void *)user != dev) {
+        CK(cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// operator tier
+// ------------------------------------------------------------------------------------------------
+static int spectral_op(xfb_handle h, int op, const float *in, float *out)
+{
+    if (!h || !in || !out) return fail(XFB_E_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(cpx) * h->hgrids;
+    const void *din;
+    if (stage_in(h, in, h->ref_a, bytes, &din)) return XFB_E_CUDA;
+    void *dout = stage_out_target(out, h->ref_b);
+    if (launch_pw(h, op, (const cpx *)din, h->hy, (cpx *)dout, h->hy, h->hy)) return XFB_E_CUDA;
+    return stage_out(h, out, dout, bytes);
+}
+
+extern "C" int xfb_gradx(xfb_handle h, const float *in, float *out) { return spectral_op(h, OP_GRADX, in, out); }
+extern "C" int xfb_grady(xfb_handle h, const float *in, float *out) { return spectral_op(h, OP_GRADY, in, out); }
+extern "C" int xfb_laplacian(xfb_handle h, const float *in, float *out) { return spectral_op(h, OP_LAP, in, out); }
+extern "C" int xfb_invert_laplacian(xfb_handle h, const float *in, float *out) { return spectral_op(h, OP_INVLAP, in, out); }
+extern "C" int xfb_dealias(xfb_handle h, const float *in, float *out) { return spectral_op(h, OP_DEALIAS, in, out); }
+
+extern "C" int xfb_get_table(xfb_handle h, int which, float *out)
+{
+    if (!h || !out) return fail(XFB_E_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    if (which == XFB_TAB_GRADX) { CK(cudaMemcpy(out, h->kx, sizeof(float) * h->nx, cudaMemcpyDeviceToHost)); return 0; }
+    if (which == XFB_TAB_GRADY) { CK(cudaMemcpy(out, h->ky, sizeof(float) * h->hy, cudaMemcpyDeviceToHost)); return 0; }
+    if (which < XFB_TAB_LAP || which > XFB_TAB_MASK) return fail(XFB_E_ARG, "xfb_get_table: bad table id %d", which);
+    float *d = (float *)h->ref_a;
+    const long long total = (long long)h->hgrids;
+    table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(d, which, h->nx, h->hy, h->kx2, h->ky2, h->mask_kd);
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaMemcpyAsync(out, d, sizeof(float) * h->hgrids, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- 2-D transforms on device buffers ---------------------------------------------------------
+static void fill_row(xfb_handle h, RowParams &p, int nrows)
+{
+    memset(&p, 0, sizeof(p));
+    p.tw = h->tw; p.twn = h->twn; p.nrows = nrows; p.pitch = h->pitch;
+    p.scale = 1.0f / (float)((double)h->nx * (double)h->ny);
+}
+
+static void fill_col(xfb_handle h, ColParams &p)
+{
+    memset(&p, 0, sizeof(p));
+    p.tw = h->tw; p.twn = h->twn; p.kx = h->kx; p.ky = h->ky; p.kx2 = h->kx2; p.ky2 = h->ky2;
+    p.pitch = h->pitch; p.member_stride = (long long)h->hpad; p.ny = h->ny; p.mask_kd = h->mask_kd; p.nu = h->nu;
+}
+
+// real [nx][ny] (device) -> padded spectrum (device), via `tmp` (padded)
+static int fwd2d(xfb_handle h, const float *real_in, cpx *tmp, cpx *spec_out)
+{
+    RowParams r; fill_row(h, r, h->nx);
+    r.real_in = real_in; r.spec_out = tmp;
+    CKL(h, launch_row(h->ny, ROW_R2C, r, h->stream));
+    ColParams c; fill_col(h, c);
+    c.jint = tmp; c.z0 = spec_out;
+    CKL(h, launch_col(h->nx, COL_FWD, c, 1, h->stream));
+    return 0;
+}
+
+// padded spectrum (device) -> real [nx][ny] (device), scaled by `scale`; spec_in is preserved
+static int inv2d(xfb_handle h, const cpx *spec_in, cpx *tmp, float *real_out, float scale, int negate)
+{
+    ColParams c; fill_col(h, c);
+    c.inv_in = spec_in; c.t_out[0] = tmp;
+    CKL(h, launch_col(h->nx, COL_INV, c, 1, h->stream));
+    RowParams r; fill_row(h, r, h->nx);
+    r.spec_in[0] = tmp; r.real_out = real_out; r.scale = scale; r.negate = negate;
+    CKL(h, launch_row(h->ny, ROW_C2R, r, h->stream));
+    return 0;
+}
+
+extern "C" int xfb_r2c(xfb_handle h, const float *real_in, float *spec_out)
+{
+    if (!h || !real_in || !spec_out) return fail(XFB_E_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    const void *din;
+    if (stage_in(h, real_in, h->real_a, sizeof(float) * h->grids, &din)) return XFB_E_CUDA;
+    if (fwd2d(h, (const float *)din, h->spec_a, h->spec_b)) return XFB_E_CUDA;
+    void *dout = stage_out_target(spec_out, h->ref_a);
+    if (launch_pw(h, OP_COPY, h->spec_b, h->pitch, (cpx *)dout, h->hy, h->hy)) return XFB_E_CUDA;
+    return stage_out(h, spec_out, dout, sizeof(cpx) * h->hgrids);
+}
+
+extern "C" int xfb_c2r(xfb_handle h, const float *spec_in, float *real_out)
+{
+    if (!h || !spec_in || !real_out) return fail(XFB_E_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    const void *din;
+    if (stage_in(h, spec_in, h->ref_a, sizeof(cpx) * h->hgrids, &din)) return XFB_E_CUDA;
+    if (launch_pw(h, OP_COPY, (const cpx *)din, h->hy, h->spec_a, h->pitch, h->hy)) return XFB_E_CUDA;
+    void *dout = stage_out_target(real_out, h->real_a);
+    if (inv2d(h, h->spec_a, h->spec_b, (float *)dout, 1.0f, 0)) return XFB_E_CUDA;
+    return stage_out(h, real_out, dout, sizeof(float) * h->grids);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stepper tier
+// ------------------------------------------------------------------------------------------------
+static int check_member(xfb_handle h, int member)
+{
+    if (!h) return fail(XFB_E_ARG, "null handle");
+    if (member < 0 || member >= h->batch) return fail(XFB_E_ARG, "member %d out of range [0,%d)", member, h->batch);
+    return 0;
+}
+
+extern "C" int xfb_set_vorticity(xfb_handle h, int member, const float *vort)
+{
+    if (check_member(h, member)) return XFB_E_ARG;
+    if (!vort) return fail(XFB_E_ARG, "null vorticity");
+    CK(cudaSetDevice(h->device));
+    const void *din;
+    if (stage_in(h, vort, h->real_a, sizeof(float) * h->grids, &din)) return XFB_E_CUDA;
+    if (fwd2d(h, (const float *)din, h->spec_a, h->z0 + (size_t)member * h->hpad)) return XFB_E_CUDA;
+    h->have_state = true;
+    h->tf_valid = false;
+    if (!is_device_ptr(vort)) CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int xfb_set_spectrum(xfb_handle h, int member, const float *spec)
+{
+    if (check_member(h, member)) return XFB_E_ARG;
+    if (!spec) return fail(XFB_E_ARG, "null spectrum");
+    CK(cudaSetDevice(h->device));
+    const void *din;
+    if (stage_in(h, spec, h->ref_a, sizeof(cpx) * h->hgrids, &din)) return XFB_E_CUDA;
+    if (launch_pw(h, OP_COPY, (const cpx *)din, h->hy, h->z0 + (size_t)member * h->hpad, h->pitch, h->hy)) return XFB_E_CUDA;
+    h->have_state = true;
+    h->tf_valid = false;
+    if (!is_device_ptr(spec)) CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int xfb_get_spectrum(xfb_handle h, int member, float *spec)
+{
+    if (check_member(h, member)) return XFB_E_ARG;
+    if (!spec) return fail(XFB_E_ARG, "null spectrum");
+    if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_spectrum before xfb_set_vorticity");
+    CK(cudaSetDevice(h->device));
+    void *dout = stage_out_target(spec, h->ref_a);
+    if (launch_pw(h, OP_COPY, h->z0 + (size_t)member * h->hpad, h->pitch, (cpx *)dout, h->hy, h->hy)) return XFB_E_CUDA;
+    return stage_out(h, spec, dout, sizeof(cpx) * h->hgrids);
+}
+
+extern "C" int xfb_set_source(xfb_handle h, int member, const float *src)
+{
+    if (check_member(h, member)) return XFB_E_ARG;
+    CK(cudaSetDevice(h->device));
+    if (!h->src) {
+        if (!src) return 0;
+        if (dev_alloc((void **)&h->src, sizeof(float) * h->grids * h->batch)) return XFB_E_CUDA;
+        CK(cudaMemsetAsync(h->src, 0, sizeof(float) * h->grids * h->batch, h->stream));
+    }
+    float *dst = h->src + (size_t)member * h->grids;
+    if (!src) {
+        CK(cudaMemsetAsync(dst, 0, sizeof(float) * h->grids, h->stream));
+    } else {
+        CK(cudaMemcpyAsync(dst, src, sizeof(float) * h->grids,
+                           is_device_ptr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        h->has_src = true;
+        if (!is_device_ptr(src)) CK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+extern "C" int xfb_step(xfb_handle h, int nsteps, float dt)
+{
+    if (!h) return fail(XFB_E_ARG, "null handle");
+    if (nsteps < 0) return fail(XFB_E_ARG, "negative step count");
+    if (!h->have_state) return fail(XFB_E_STATE, "xfb_step before xfb_set_vorticity");
+    CK(cudaSetDevice(h->device));
+    ColParams c; fill_col(h, c);
+    c.jint = h->jint; c.z0 = h->z0; c.zk = h->zk; c.acc = h->acc;
+    for (int f = 0; f < 4; ++f) c.t_out[f] = h->t[f];
+    c.dt = dt;
+    RowParams r; fill_row(h, r, h->nx * h->batch);
+    for (int f = 0; f < 4; ++f) r.spec_in[f] = h->t[f];
+    r.real_in = h->has_src ? h->src : nullptr;
+    r.spec_out = h->jint;
+    if (nsteps > 0 && !h->tf_valid) {
+        CKL(h, launch_col(h->nx, COL_PRO, c, h->batch, h->stream));
+        h->tf_valid = true;
+    }
+    for (int s = 0; s < nsteps; ++s) {
+        for (int k = 1; k <= 4; ++k) {
+            CKL(h, launch_row(h->ny, ROW_JAC, r, h->stream));
+            c.stage = k;
+            c.dt_stage = (k == 3) ? dt : dt / 2.0f;          // main.cpp:296,299,302
+            CKL(h, launch_col(h->nx, COL_STEP, c, h->batch, h->stream));
+        }
+    }
+    return 0;
+}
+
+// derived spectral field of member -> physical field in `dout` (device), reference normalisation
+static int derived_field(xfb_handle h, int member, int which, float *dout)
+{
+    const cpx *z = h->z0 + (size_t)member * h->hpad;
+    const float scale = 1.0f / (float)((double)h->nx * (double)h->ny);
+    const int P = h->pitch;
+    switch (which) {
+    case XFB_VORT:
+        return inv2d(h, z, h->spec_b, dout, scale, 0);
+    case XFB_PSI:
+        if (launch_pw(h, OP_INVLAP, z, P, h->spec_a, P, P)) return XFB_E_CUDA;
+        return inv2d(h, h->spec_a, h->spec_b, dout, scale, 0);
+    case XFB_U:
+        if (launch_pw(h, OP_INVLAP, z, P, h->spec_a, P, P)) return XFB_E_CUDA;
+        if (launch_pw(h, OP_GRADY, h->spec_a, P, h->spec_a, P, P)) return XFB_E_CUDA;
+        return inv2d(h, h->spec_a, h->spec_b, dout, scale, 1);
+    case XFB_V:
+        if (launch_pw(h, OP_INVLAP, z, P, h->spec_a, P, P)) return XFB_E_CUDA;
+        if (launch_pw(h, OP_GRADX, h->spec_a, P, h->spec_a, P, P)) return XFB_E_CUDA;
+        return inv2d(h, h->spec_a, h->spec_b, dout, scale, 0);
+    case XFB_DVORTDX:
+        if (launch_pw(h, OP_GRADX, z, P, h->spec_a, P, P)) return XFB_E_CUDA;
+        return inv2d(h, h->spec_a, h->spec_b, dout, scale, 0);
+    case XFB_DVORTDY:
+        if (launch_pw(h, OP_GRADY, z, P, h->spec_a, P, P)) return XFB_E_CUDA;
+        return inv2d(h, h->spec_a, h->spec_b, dout, scale, 0);
+    }
+    return fail(XFB_E_ARG, "bad field id %d", which);
+}
+
+// second derivatives of psi for the diagnostics: which = 0 psi_xy, 1 psi_xx, 2 psi_yy
+static int psi_second(xfb_handle h, int member, int which, float *dout)
+{
+    const cpx *z = h->z0 + (size_t)member * h->hpad;
+    const float scale = 1.0f / (float)((double)h->nx * (double)h->ny);
+    const int P = h->pitch;
+    if (launch_pw(h, OP_INVLAP, z, P, h->spec_a, P, P)) return XFB_E_CUDA;
+    if (launch_pw(h, which == 2 ? OP_GRADY : OP_GRADX, h->spec_a, P, h->spec_a, P, P)) return XFB_E_CUDA;
+    if (launch_pw(h, which == 1 ? OP_GRADX : OP_GRADY, h->spec_a, P, h->spec_a, P, P)) return XFB_E_CUDA;
+    return inv2d(h, h->spec_a, h->spec_b, dout, scale, 0);
+}
+
+// filamentation time and deformation factor from psi_xy, psi_xx, psi_yy (oracle: orc_diagnostics)
+__global__ void diag_kernel(const float *pxy, const float *pxx, const float *pyy, float *out, long long n, int which)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float s1 = __fmul_rn(-2.0f, pxy[i]), s2 = __fsub_rn(pxx[i], pyy[i]), z = __fadd_rn(pxx[i], pyy[i]);
+    const float ss = __fadd_rn(__fmul_rn(s1, s1), __fmul_rn(s2, s2)), zz = __fmul_rn(z, z);
+    const float q = __fsub_rn(ss, zz), den = __fadd_rn(ss, zz);
+    if (which == XFB_TFIL) out[i] = (q > 0.0f) ? __fdiv_rn(2.0f, __fsqrt_rn(q)) : 0.0f;
+    else out[i] = (den > 0.0f) ? __fdiv_rn(q, den) : 0.0f;
+}
+
+extern "C" int xfb_get_field(xfb_handle h, int member, int which, float *out)
+{
+    if (check_member(h, member)) return XFB_E_ARG;
+    if (!out) return fail(XFB_E_ARG, "null output");
+    if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_field before xfb_set_vorticity");
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(float) * h->grids;
+    if (which == XFB_SRC) {
+        if (!h->src) {
+            if (is_device_ptr(out)) { CK(cudaMemsetAsync(out, 0, bytes, h->stream)); }
+            else memset(out, 0, bytes);
+            return 0;
+        }
+        CK(cudaMemcpyAsync(out, h->src + (size_t)member * h->grids, bytes,
+                           is_device_ptr(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    float *dout = (float *)stage_out_target(out, h->real_a);
+    if (which == XFB_TFIL || which == XFB_DEFORM) {
+        if (psi_second(h, member, 0, h->real_b)) return XFB_E_CUDA;
+        if (psi_second(h, member, 1, h->real_c)) return XFB_E_CUDA;
+        float *pyy = dout;   // psi_yy lands in the output buffer, then is overwritten in place
+        if (psi_second(h, member, 2, pyy)) return XFB_E_CUDA;
+        const long long n = (long long)h->grids;
+        diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->real_b, h->real_c, pyy, dout, n, which);
+        CK(cudaGetLastError());
+        h->launches++;
+    } else {
+        if (derived_field(h, member, which, dout)) return XFB_E_CUDA;
+    }
+    return stage_out(h, out, dout, bytes);
+}
+
+// histogram of area and |grad zeta|^2 over tracer bins (oracle: orc_keff_hist)
+__global__ void keff_hist_kernel(const float *c, const float *gx, const float *gy, long long n, int nbins, float cmin,
+                                 float scale, double da, double *area, double *grad2)
+{
+    extern __shared__ double sh[];
+    double *sa = sh, *sg = sh + nbins;
+    for (int b = threadIdx.x; b < 2 * nbins; b += blockDim.x) sh[b] = 0.0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int b = (int)floorf(__fmul_rn(__fsub_rn(c[i], cmin), scale));
+        b = b < 0 ? 0 : (b >= nbins ? nbins - 1 : b);
+        const float g2 = __fadd_rn(__fmul_rn(gx[i], gx[i]), __fmul_rn(gy[i], gy[i]));
+        atomicAdd(&sa[b], da);
+        atomicAdd(&sg[b], (double)g2 * da);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+        if (sa[b] != 0.0) atomicAdd(&area[b], sa[b]);
+        if (sg[b] != 0.0) atomicAdd(&grad2[b], sg[b]);
+    }
+}
+
+extern "C" int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cmax, double *area, double *grad2)
+{
+    if (check_member(h, member)) return XFB_E_ARG;
+    if (!area || !grad2 || nbins < 1 || nbins > 2048 || !(cmax > cmin)) return fail(XFB_E_ARG, "bad histogram arguments");
+    if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_keff_hist before xfb_set_vorticity");
+    CK(cudaSetDevice(h->device));
+    if (derived_field(h, member, XFB_VORT, h->real_a)) return XFB_E_CUDA;
+    if (derived_field(h, member, XFB_DVORTDX, h->real_b)) return XFB_E_CUDA;
+    if (derived_field(h, member, XFB_DVORTDY, h->real_c)) return XFB_E_CUDA;
+    double *d = (double *)h->ref_a;
+    CK(cudaMemsetAsync(d, 0, sizeof(double) * 2 * nbins, h->stream));
+    const double da = ((double)h->lx / h->nx) * ((double)h->ly / h->ny);
+    const float scale = (float)nbins / (cmax - cmin);
+    keff_hist_kernel<<<296, 256, sizeof(double) * 2 * nbins, h->stream>>>(h->real_a, h->real_b, h->real_c, (long long)h->grids,
+                                                                           nbins, cmin, scale, da, d, d + nbins);
+    CK(cudaGetLastError());
+    h->launches++;
+    std::vector<double> host(2 * (size_t)nbins);
+    CK(cudaMemcpyAsync(host.data(), d, sizeof(double) * 2 * nbins, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(area, host.data(), sizeof(double) * nbins);
+    memcpy(grad2, host.data() + nbins, sizeof(double) * nbins);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pressure inversion (invert_pres.cpp:132-187)
+// ------------------------------------------------------------------------------------------------
+__global__ void gauss_curv_kernel(const float *dx2, const float *dy2, const float *dxdy, float *out, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = __fsub_rn(__fmul_rn(dx2[i], dy2[i]), __fmul_rn(dxdy[i], dxdy[i]));     // invert_pres.cpp:159
+}
+
+// lap_pres_c = rho * (f * tmp_c + 2.0 * lap_pres_c), float64 intermediates        (invert_pres.cpp:166-169)
+__global__ void pres_source_kernel(const cpx *lap_psi, cpx *lap_pres, long long n, float rho, float f)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const cpx a = lap_psi[i], b = lap_pres[i];
+    const float fa_x = __fmul_rn(f, a.x), fa_y = __fmul_rn(f, a.y);
+    lap_pres[i] = mk((float)((double)rho * ((double)fa_x + 2.0 * (double)b.x)),
+                     (float)((double)rho * ((double)fa_y + 2.0 * (double)b.y)));
+}
+
+__global__ void sub_ref_kernel(float *p, long long n, size_t ref)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float r;
+    if (threadIdx.x == 0) r = p[ref];
+    __syncthreads();
+    // all blocks read p[ref] before any block can overwrite it only if it is excluded here;
+    // the reference element itself is handled by a second launch
+    if (i < n && (size_t)i != ref) p[i] = __fsub_rn(p[i], r);
+}
+
+__global__ void zero_one_kernel(float *p, size_t ref) { p[ref] = __fsub_rn(p[ref], p[ref]); }
+
+extern "C" int xfb_invert_pres(xfb_handle h, const float *psi, float *pres, size_t ref_x, size_t ref_y, float rho, float f)
+{
+    if (!h || !psi || !pres) return fail(XFB_E_ARG, "null argument");
+    const size_t ref = ref_x + (size_t)h->nx * ref_y;     // invert_pres.cpp:182 (x + XPTS*y, as written there)
+    if (ref >= h->grids) return fail(XFB_E_ARG, "reference point out of range");
+    CK(cudaSetDevice(h->device));
+    const int P = h->pitch;
+    const long long n = (long long)h->grids, hn = (long long)h->hpad;
+    const float scale = 1.0f / (float)((double)h->nx * (double)h->ny);
+    const void *din;
+    if (stage_in(h, psi, h->real_a, sizeof(float) * h->grids, &din)) return XFB_E_CUDA;
+    // psi_c lives in t[0]; t[1..3] and jint are scratch (the stepper's prologue is invalidated)
+    h->tf_valid = false;
+    cpx *psi_c = h->t[0], *w1 = h->t[1], *w2 = h->t[2], *lap_pres = h->t[3];
+    if (fwd2d(h, (const float *)din, h->spec_a, psi_c)) return XFB_E_CUDA;                       // :135
+    // d2/dx2                                                                                      :139-140,148,153
+    if (launch_pw(h, OP_GRADX, psi_c, P, w1, P, P) || launch_pw(h, OP_GRADX, w1, P, w1, P, P) ||
+        launch_pw(h, OP_DEALIAS, w1, P, w1, P, P) || inv2d(h, w1, h->spec_b, h->real_a, scale, 0))
+        return XFB_E_CUDA;
+    // d2/dy2                                                                                      :142-143,149,154
+    if (launch_pw(h, OP_GRADY, psi_c, P, w2, P, P) || launch_pw(h, OP_GRADY, w2, P, w1, P, P) ||
+        launch_pw(h, OP_DEALIAS, w1, P, w1, P, P) || inv2d(h, w1, h->spec_b, h->real_b, scale, 0))
+        return XFB_E_CUDA;
+    // d2/dxdy = gradx(grady(psi))                                                                 :145,150,155
+    if (launch_pw(h, OP_GRADX, w2, P, w1, P, P) || launch_pw(h, OP_DEALIAS, w1, P, w1, P, P) ||
+        inv2d(h, w1, h->spec_b, h->real_c, scale, 0))
+        return XFB_E_CUDA;
+    gauss_curv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->real_a, h->real_b, h->real_c, h->real_a, n);
+    CK(cudaGetLastError()); h->launches++;
+    if (fwd2d(h, h->real_a, h->spec_a, lap_pres)) return XFB_E_CUDA;                               // :161
+    if (launch_pw(h, OP_LAP, psi_c, P, w1, P, P)) return XFB_E_CUDA;                               // :164
+    pres_source_kernel<<<(unsigned)((hn + 255) / 256), 256, 0, h->stream>>>(w1, lap_pres, hn, rho, f);
+    CK(cudaGetLastError()); h->launches++;
+    if (launch_pw(h, OP_INVLAP, lap_pres, P, w1, P, P)) return XFB_E_CUDA;                         // :171
+    float *dout = (float *)stage_out_target(pres, h->real_b);
+    if (inv2d(h, w1, h->spec_b, dout, scale, 0)) return XFB_E_CUDA;                                // :172
+    sub_ref_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dout, n, ref);              // :182-185
+    CK(cudaGetLastError()); h->launches++;
+    zero_one_kernel<<<1, 1, 0, h->stream>>>(dout, ref);
+    CK(cudaGetLastError()); h->launches++;
+    return stage_out(h, pres, dout, sizeof(float) * h->grids);
+}

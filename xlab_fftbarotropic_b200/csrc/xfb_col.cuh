@@ -1,0 +1,215 @@
+// xfb_col.cuh -- K-COL: transforms along x (the strided direction) on tiles of W adjacent
+// spectral columns, with every pointwise spectral operator of the reference fused around them.
+//
+// One launch of COL_STEP replaces, for its column tile (file:line in /root/reference/src):
+//   first-dimension half of the r2c of the tendency                  main.cpp:237
+//   fop.laplacian + `dvortdt_c += lvort_c * NU`                      main.cpp:148,240-243 ; fftwfop.cpp:105-110
+//   fop.dealiase -> rk_k                                             main.cpp:296-306     ; fftwfop.cpp:119-124
+//   evolve() / final RK4 combine                                     main.cpp:246-251,309-312
+//   memcpy(vort_c0 <- vort_c)                                        main.cpp:286 (eliminated)
+//   fop.gradx, fop.grady, fop.invertLaplacian of the NEXT stage      main.cpp:151,165,179,198,212 ; fftwfop.cpp:87-117
+//   first-dimension half of the four c2r                             main.cpp:154,168,200,214
+// The wavenumber/Laplacian/mask tables of fftwfop.cpp:5-79 are never materialised as H-sized
+// arrays: kx[NX], ky[pitch] and their float64 squares are tiny tables, the mask is integer math.
+#pragma once
+#include "xfb_fft.cuh"
+
+namespace xfb {
+
+enum { COL_FWD = 0, COL_INV = 1, COL_STEP = 2, COL_PRO = 3 };
+
+struct ColParams {
+    const cpx *jint;      // FWD/STEP: y-transformed lines [NX][pitch]
+    cpx *z0;              // spectral state at the start of the step (FWD writes it)
+    cpx *zk;              // stage state
+    cpx *acc;             // running RK4 sum r1 + 2 r2 + 2 r3
+    cpx *t_out[4];        // x-inverse-transformed i kx Z, i ky Z, i ky Psi, i kx Psi ; INV: [0]
+    const cpx *inv_in;    // INV: spectrum to transform
+    const cpx *tw;
+    int twn;
+    const float *kx;      // [NX]    gradx_coe
+    const float *ky;      // [pitch] grady_coe (pad columns continue the formula)
+    const double *kx2;    // [NX]    (double)kx*kx
+    const double *ky2;    // [pitch]
+    int pitch;
+    long long member_stride;   // complex elements between ensemble members
+    int ny;               // for the mask reflection nothing is needed in y; kept for clarity
+    double mask_kd;       // generalized_wavenumber_square (fftwfop.cpp:57), as stored in float
+    float nu;
+    float dt;             // full step
+    float dt_stage;       // dt/2, dt/2, dt for stages 1..3
+    int stage;            // 1..4
+};
+
+template <int NX, int W>
+struct ColCfg {
+    static constexpr int G = NX / 16;
+    static constexpr int VT = G * W;                          // butterfly threads per tile
+    static constexpr int NIT = (VT >= 64) ? 2 : 1;
+    static constexpr int THREADS = VT / NIT;
+    static constexpr int SMEM = LinePlan<NX>::PADDED * W * (int)sizeof(cpx);
+    static_assert(THREADS <= 1024 && THREADS >= 16, "bad column tile");
+};
+
+// -(kx^2 + ky^2) narrowed to float, summed in float64 like pow(float,2)+pow(float,2) (fftwfop.cpp:42-45)
+__device__ __forceinline__ float lap_coe(const double kx2, const double ky2) { return (float)(-(kx2 + ky2)); }
+
+template <int NX, int W, int NIT>
+__device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&t)[NIT], const int (&c)[NIT],
+                                        const LineTw<NX> (&tw)[NIT])
+{
+    typedef LinePlan<NX> P;
+    int ns = 1;
+#pragma unroll
+    for (int p = 0; p < P::N16; ++p) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) pass16_compute<NX>(v[it], p, tw[it]);
+        if (p != P::NPASS - 1) {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) exchange_write<W>(v[it], sm, t[it], c[it], ns);
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) exchange_read<P::G, W>(v[it], sm, t[it], c[it]);
+            __syncthreads();
+        }
+        ns *= 16;
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) rem_pass<NX>(v[it], tw[it]);
+}
+
+template <int NX, int W, int MODE>
+__global__ void __launch_bounds__(ColCfg<NX, W>::THREADS, (ColCfg<NX, W>::THREADS <= 256) ? 2 : 1)
+col_kernel(const ColParams p)
+{
+    typedef ColCfg<NX, W> C;
+    constexpr int G = C::G, NIT = C::NIT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cpx *sm = reinterpret_cast<cpx *>(smem_raw);
+
+    const int j0 = blockIdx.x * W;
+    const size_t moff = (size_t)blockIdx.y * (size_t)p.member_stride;
+
+    int t[NIT], c[NIT];
+    LineTw<NX> tw[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int vt = it * C::THREADS + threadIdx.x;
+        c[it] = vt % W;
+        t[it] = vt / W;
+        tw[it].init(p.tw, p.twn, t[it]);
+    }
+
+    cpx v[NIT][16];
+
+    // ------------------------------------------------------------------ forward + epilogue
+    if (MODE == COL_FWD || MODE == COL_STEP) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const cpx *src = p.jint + moff + j0 + c[it];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[it][k] = __ldg(src + (size_t)(t[it] + k * G) * p.pitch);
+        }
+        col_fft<NX, W, NIT>(v, sm, t, c, tw);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int j = j0 + c[it];
+            const double ky2 = p.ky2[j];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int i = t[it] + k * G;
+                const size_t e = moff + (size_t)i * p.pitch + j;
+                const cpx X = v[it][k];
+                if (MODE == COL_FWD) {
+                    p.z0[e] = X;
+                } else {
+                    const cpx z0v = p.z0[e];
+                    const cpx zkv = (p.stage == 1) ? z0v : p.zk[e];
+                    const float lap = lap_coe(p.kx2[i], ky2);
+                    // dvortdt_c += (vort_c * laplacian_coe) * NU
+                    const float tx = __fadd_rn(X.x, __fmul_rn(__fmul_rn(zkv.x, lap), p.nu));
+                    const float ty = __fadd_rn(X.y, __fmul_rn(__fmul_rn(zkv.y, lap), p.nu));
+                    // dealiasing mask: (i^2 + j^2 >= kd) ? 0 : 1 with i reflected above NX/2
+                    const long long ii = (i <= NX / 2) ? i : NX - i;
+                    const float m = ((double)(ii * ii + (long long)j * j) >= p.mask_kd) ? 0.0f : 1.0f;
+                    const float rx = __fmul_rn(tx, m), ry = __fmul_rn(ty, m);
+                    cpx zn;
+                    if (p.stage == 4) {
+                        const cpx a = p.acc[e];
+                        zn.x = __fadd_rn(z0v.x, __fdiv_rn(__fmul_rn(__fadd_rn(a.x, rx), p.dt), 6.0f));
+                        zn.y = __fadd_rn(z0v.y, __fdiv_rn(__fmul_rn(__fadd_rn(a.y, ry), p.dt), 6.0f));
+                        p.z0[e] = zn;
+                    } else {
+                        cpx an;
+                        if (p.stage == 1) {
+                            an = mk(rx, ry);
+                        } else {
+                            const cpx a = p.acc[e];
+                            an = mk(__fadd_rn(a.x, __fmul_rn(2.0f, rx)), __fadd_rn(a.y, __fmul_rn(2.0f, ry)));
+                        }
+                        p.acc[e] = an;
+                        zn.x = __fadd_rn(z0v.x, __fmul_rn(rx, p.dt_stage));
+                        zn.y = __fadd_rn(z0v.y, __fmul_rn(ry, p.dt_stage));
+                        p.zk[e] = zn;
+                    }
+                }
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------ plain inverse
+    if (MODE == COL_INV) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const cpx *src = p.inv_in + moff + j0 + c[it];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[it][k] = cswap(__ldg(src + (size_t)(t[it] + k * G) * p.pitch));
+        }
+        col_fft<NX, W, NIT>(v, sm, t, c, tw);
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            cpx *dst = p.t_out[0] + moff + j0 + c[it];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dst[(size_t)(t[it] + k * G) * p.pitch] = cswap(v[it][k]);
+        }
+    }
+
+    // ------------------------------------------------------------------ prologue + 4 inverse
+    if (MODE == COL_STEP || MODE == COL_PRO) {
+        // the state this thread just wrote (stage 4 / PRO: z0, else zk) is re-read from L1/L2
+        const cpx *zsrc = (MODE == COL_PRO || p.stage == 4) ? p.z0 : p.zk;
+#pragma unroll 1
+        for (int f = 0; f < 4; ++f) {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int j = j0 + c[it];
+                const float ky = __ldg(p.ky + j);
+                const double ky2 = __ldg(p.ky2 + j);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int i = t[it] + k * G;
+                    cpx z = zsrc[moff + (size_t)i * p.pitch + j];
+                    if (f >= 2) {
+                        // psi_c = vort_c / laplacian_coe_inverse, (0,0) entry = 1      (fftwfop.cpp:43,112-117)
+                        const float li = (i == 0 && j == 0) ? 1.0f : lap_coe(__ldg(p.kx2 + i), ky2);
+                        z = mk(__fdiv_rn(z.x, li), __fdiv_rn(z.y, li));
+                    }
+                    // f = 0: i kx Z, 1: i ky Z, 2: i ky Psi (u before negation), 3: i kx Psi (v)
+                    const float kk = (f == 0 || f == 3) ? __ldg(p.kx + i) : ky;
+                    const cpx g = mk(__fmul_rn(-z.y, kk), __fmul_rn(z.x, kk));
+                    v[it][k] = cswap(g);
+                }
+            }
+            col_fft<NX, W, NIT>(v, sm, t, c, tw);
+            cpx *outp = p.t_out[f];
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                cpx *dst = outp + moff + j0 + c[it];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) dst[(size_t)(t[it] + k * G) * p.pitch] = cswap(v[it][k]);
+            }
+        }
+    }
+}
+
+}  // namespace xfb

@@ -1,0 +1,245 @@
+// xfb_fft.cuh -- register/shared-memory FFT building blocks for sm_100a.
+//
+// Scheme (validated against numpy in the design prototype, see DESIGN.md "FFT engine"):
+//   * one "butterfly thread" owns R = 16 complex values of a line of length L, at positions
+//     t + k*G (G = L/16, k = 0..15) -- in EVERY pass and at the end of the transform, so
+//     consecutive transforms (c2r -> Jacobian -> r2c, forward -> epilogue -> inverse) chain
+//     in registers without a re-layout;
+//   * Stockham autosort passes: radix-16 passes first, the remainder radix (2/4/8) last;
+//     the first pass reads straight from global memory (coalesced across t), the last
+//     pass leaves natural-order output in registers for a coalesced global store;
+//     only the exchanges between passes go through shared memory (padded: pos + pos/16,
+//     conflict-free for 8-byte accesses);
+//   * twiddles: one table lookup per thread per pass (kept in registers for the whole
+//     kernel), powers by a depth-4 multiplication tree;
+//   * inverse transforms use the swap trick  ifft(x) = swap(fft(swap(x))).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace xfb {
+
+typedef float2 cpx;
+
+__device__ __forceinline__ cpx mk(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return mk(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return mk(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cpx cmul(cpx a, cpx b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cpx cconj(cpx a) { return mk(a.x, -a.y); }
+__device__ __forceinline__ cpx cswap(cpx a) { return mk(a.y, a.x); }
+__device__ __forceinline__ cpx mul_negi(cpx a) { return mk(a.y, -a.x); }   // a * (-i)
+__device__ __forceinline__ cpx mul_i(cpx a) { return mk(-a.y, a.x); }      // a * (+i)
+
+#define XFB_C8 0.70710678118654752440f
+#define XFB_C16 0.92387953251128675613f
+#define XFB_S16 0.38268343236508977173f
+
+// ---- forward DFTs in registers, natural order in and out ---------------------------------
+
+__device__ __forceinline__ void dft2(cpx &a, cpx &b)
+{
+    cpx t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+
+__device__ __forceinline__ void dft4(cpx &a0, cpx &a1, cpx &a2, cpx &a3)
+{
+    cpx t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_negi(csub(a1, a3));
+    a0 = cadd(t0, t2);
+    a1 = cadd(t1, t3);
+    a2 = csub(t0, t2);
+    a3 = csub(t1, t3);
+}
+
+__device__ __forceinline__ void dft8(cpx (&v)[8])
+{
+    // even/odd split: X[k] = E[k] + W8^k O[k], X[k+4] = E[k] - W8^k O[k]
+    cpx e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+    cpx o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+    dft4(e0, e1, e2, e3);
+    dft4(o0, o1, o2, o3);
+    o1 = mk((o1.x + o1.y) * XFB_C8, (o1.y - o1.x) * XFB_C8);     // * (1 - i)/sqrt2
+    o2 = mul_negi(o2);
+    o3 = mk((o3.y - o3.x) * XFB_C8, -(o3.x + o3.y) * XFB_C8);    // * (-1 - i)/sqrt2
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+    v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+__device__ __forceinline__ void dft16(cpx (&v)[16])
+{
+    // n = c + 4a, q = k + 4m:  X[k+4m] = sum_c W4^(cm) [ W16^(ck) sum_a v[c+4a] W4^(ak) ]
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dft4(v[c], v[c + 4], v[c + 8], v[c + 12]);
+    // now v[c + 4k] holds u[c][k]; apply W16^(ck)
+    const cpx w1 = mk(XFB_C16, -XFB_S16), w3 = mk(XFB_S16, -XFB_C16);
+    v[1 + 4] = cmul(v[1 + 4], w1);                                                         // (1,1) W16^1
+    v[1 + 8] = mk((v[1 + 8].x + v[1 + 8].y) * XFB_C8, (v[1 + 8].y - v[1 + 8].x) * XFB_C8); // (1,2) W16^2
+    v[1 + 12] = cmul(v[1 + 12], w3);                                                       // (1,3) W16^3
+    v[2 + 4] = mk((v[2 + 4].x + v[2 + 4].y) * XFB_C8, (v[2 + 4].y - v[2 + 4].x) * XFB_C8); // (2,1) W16^2
+    v[2 + 8] = mul_negi(v[2 + 8]);                                                         // (2,2) W16^4
+    v[2 + 12] = mk((v[2 + 12].y - v[2 + 12].x) * XFB_C8, -(v[2 + 12].x + v[2 + 12].y) * XFB_C8); // (2,3) W16^6
+    v[3 + 4] = cmul(v[3 + 4], w3);                                                         // (3,1) W16^3
+    v[3 + 8] = mk((v[3 + 8].y - v[3 + 8].x) * XFB_C8, -(v[3 + 8].x + v[3 + 8].y) * XFB_C8); // (3,2) W16^6
+    v[3 + 12] = cmul(v[3 + 12], mk(-XFB_C16, XFB_S16));                                    // (3,3) W16^9
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dft4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    // v[4k + m] holds X[k + 4m]: transpose the 4x4 index back to natural order
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int m = k + 1; m < 4; ++m) {
+            cpx t = v[4 * k + m];
+            v[4 * k + m] = v[4 * m + k];
+            v[4 * m + k] = t;
+        }
+}
+
+// w[s] = w1^s, s = 1..15 (w[0] unused); depth-4 product tree
+__device__ __forceinline__ void pow_chain16(cpx w1, cpx (&w)[16])
+{
+    w[0] = mk(1.f, 0.f);
+    w[1] = w1;
+    w[2] = cmul(w1, w1);
+    w[3] = cmul(w[2], w1);
+    w[4] = cmul(w[2], w[2]);
+    w[5] = cmul(w[4], w1);
+    w[6] = cmul(w[3], w[3]);
+    w[7] = cmul(w[4], w[3]);
+    w[8] = cmul(w[4], w[4]);
+#pragma unroll
+    for (int s = 1; s < 8; ++s) w[8 + s] = cmul(w[8], w[s]);
+}
+
+// ---- line plan -----------------------------------------------------------------------------
+
+template <int L>
+struct LinePlan {
+    static constexpr int R = 16;
+    static constexpr int G = L / R;              // butterfly threads per line
+    static constexpr int N16 = (L >= 65536) ? 4 : (L >= 4096) ? 3 : (L >= 256) ? 2 : (L >= 16) ? 1 : 0;
+    static constexpr int P16 = (N16 == 4) ? 65536 : (N16 == 3) ? 4096 : (N16 == 2) ? 256 : (N16 == 1) ? 16 : 1;
+    static constexpr int REM = L / P16;          // remainder radix: 1, 2, 4 or 8
+    static constexpr int NPASS = N16 + (REM > 1 ? 1 : 0);
+    static constexpr int PADDED = L + L / 16;    // shared-memory positions per line
+    static_assert(L % 16 == 0 && P16 * REM == L, "line length must be 16^a * {1,2,4,8}");
+};
+
+__device__ __forceinline__ int padpos(int p) { return p + (p >> 4); }
+
+// Per-thread twiddle bases for a line of length L, from the master table
+// tw[k] = exp(-2 pi i k / TWN), k in [0, TWN) (TWN a multiple of L).
+//   b[p], p = 1..N16-1 : radix-16 pass p      exp(-2 pi i (t mod 16^p) / 16^(p+1))
+//   b[0]               : remainder pass       exp(-2 pi i t / L)
+template <int L>
+struct LineTw {
+    cpx b[4];
+    __device__ __forceinline__ void init(const cpx *__restrict__ tw, int twn, int t)
+    {
+        typedef LinePlan<L> P;
+        int ns = 16;
+#pragma unroll
+        for (int p = 1; p < P::N16; ++p) {
+            b[p] = __ldg(tw + (size_t)(t % ns) * (twn / (ns * 16)));
+            ns *= 16;
+        }
+        b[0] = (P::REM > 1) ? __ldg(tw + (size_t)t * (twn / L)) : mk(1.f, 0.f);
+    }
+};
+
+// ---- pass pieces (composed by line_fft below and by the multi-iteration column kernel) ----
+
+// radix-16 pass p: twiddle (p > 0) + butterfly
+template <int L>
+__device__ __forceinline__ void pass16_compute(cpx (&v)[16], const int p, const LineTw<L> &tw)
+{
+    if (p > 0) {
+        cpx w[16];
+        pow_chain16(tw.b[p], w);
+#pragma unroll
+        for (int s = 1; s < 16; ++s) v[s] = cmul(v[s], w[s]);
+    }
+    dft16(v);
+}
+
+// Stockham scatter of pass-p results (ns = 16^p); element address = padpos(pos) * W + c
+template <int W>
+__device__ __forceinline__ void exchange_write(const cpx (&v)[16], cpx *sm, const int t, const int c, const int ns)
+{
+    const int base = (t / ns) * ns * 16 + (t % ns);
+#pragma unroll
+    for (int s = 0; s < 16; ++s) sm[padpos(base + s * ns) * W + c] = v[s];
+}
+
+template <int G, int W>
+__device__ __forceinline__ void exchange_read(cpx (&v)[16], const cpx *sm, const int t, const int c)
+{
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = sm[padpos(t + k * G) * W + c];
+}
+
+// remainder pass, radix r = REM (last pass): butterflies q = 0..16/r-1 at j = t + q*G use register
+// slots q + s*(16/r); twiddle exp(-2 pi i j / L) = b[0] * exp(-2 pi i q / 16)
+template <int L>
+__device__ __forceinline__ void rem_pass(cpx (&v)[16], const LineTw<L> &tw)
+{
+    typedef LinePlan<L> P;
+    if (P::REM > 1) {
+        constexpr int r = (P::REM > 1) ? P::REM : 2, nb = 16 / r;
+        const float CQ[8] = {1.f, XFB_C16, XFB_C8, XFB_S16, 0.f, -XFB_S16, -XFB_C8, -XFB_C16};
+        const float SQ[8] = {0.f, -XFB_S16, -XFB_C8, -XFB_C16, -1.f, -XFB_C16, -XFB_C8, -XFB_S16};
+#pragma unroll
+        for (int q = 0; q < nb; ++q) {
+            const cpx w1 = (q == 0) ? tw.b[0] : cmul(tw.b[0], mk(CQ[q], SQ[q]));
+            if (r == 2) {
+                cpx a = v[q], b = cmul(v[q + nb], w1);
+                v[q] = cadd(a, b);
+                v[q + nb] = csub(a, b);
+            } else if (r == 4) {
+                cpx w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+                cpx a0 = v[q], a1 = cmul(v[q + nb], w1), a2 = cmul(v[q + 2 * nb], w2), a3 = cmul(v[q + 3 * nb], w3);
+                dft4(a0, a1, a2, a3);
+                v[q] = a0; v[q + nb] = a1; v[q + 2 * nb] = a2; v[q + 3 * nb] = a3;
+            } else {
+                cpx a[8];
+                cpx w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+                a[0] = v[q];
+                a[1] = cmul(v[q + nb], w1);
+                a[2] = cmul(v[q + 2 * nb], w2);
+                a[3] = cmul(v[q + 3 * nb], w3);
+                a[4] = cmul(v[q + 4 * nb], w4);
+                a[5] = cmul(v[q + 5 * nb], cmul(w4, w1));
+                a[6] = cmul(v[q + 6 * nb], cmul(w3, w3));
+                a[7] = cmul(v[q + 7 * nb], cmul(w4, w3));
+                dft8(a);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) v[q + s * nb] = a[s];
+            }
+        }
+    }
+}
+
+// Forward FFT of one line held as v[k] = x[t + k*G].  `sm` points at this line's padded
+// shared buffer; element address = (padpos(pos) * W + c).  All threads of the CTA must call
+// this together (it uses __syncthreads()).  On return v[k] = X[t + k*G].
+template <int L, int W>
+__device__ __forceinline__ void line_fft(cpx (&v)[16], cpx *sm, const int t, const int c, const LineTw<L> &tw)
+{
+    typedef LinePlan<L> P;
+    int ns = 1;
+#pragma unroll
+    for (int p = 0; p < P::N16; ++p) {
+        pass16_compute<L>(v, p, tw);
+        if (p != P::NPASS - 1) {
+            exchange_write<W>(v, sm, t, c, ns);
+            __syncthreads();
+            exchange_read<P::G, W>(v, sm, t, c);
+            __syncthreads();
+        }
+        ns *= 16;
+    }
+    rem_pass<L>(v, tw);
+}
+
+}  // namespace xfb

@@ -1,0 +1,179 @@
+// xfb_row.cuh -- K-ROW: transforms along y (the contiguous direction), one line per group of
+// NY/32 threads.  Replaces, for one row i of the grid:
+//   R2C : the last-dimension half of fftwf_plan_dft_r2c_2d   (/root/reference/src/main.cpp:126-127,237,256)
+//   C2R : the last-dimension half of fftwf_plan_dft_c2r_2d + fftwf_backward_normalize
+//         (main.cpp:129-135,37-41)
+//   JAC : four C2R (dvortdx, dvortdy, u, v: main.cpp:154,168,200,214), `u = -u` (:201), the
+//         Jacobian + source loop (:225-227) and the R2C of the tendency (:237), chained in
+//         registers -- the physical-space fields never touch HBM.
+// A real line of NY points is transformed as a complex line of L = NY/2 points plus the
+// standard split/merge step (same algebra as oracle/fftw3_shim/shim_fft.c, different code).
+#pragma once
+#include "xfb_fft.cuh"
+
+namespace xfb {
+
+enum { ROW_R2C = 0, ROW_C2R = 1, ROW_JAC = 2 };
+
+struct RowParams {
+    const cpx *spec_in[4];   // JAC: T_zx, T_zy, T_u, T_v ; C2R: [0]
+    const float *real_in;    // R2C input ; JAC: optional source term (may be null)
+    cpx *spec_out;           // R2C / JAC output (y-transformed lines)
+    float *real_out;         // C2R output
+    const cpx *tw;           // exp(-2 pi i k / twn)
+    int twn;
+    int nrows;               // NX * batch
+    int pitch;               // complex elements per spectral line (>= NY/2+1)
+    float scale;             // 1/(NX*NY) applied after every C2R (fftwf_backward_normalize)
+    int negate;              // C2R: multiply by -1 after scaling (u = -u)
+};
+
+template <int NY>
+struct RowCfg {
+    static constexpr int L = NY / 2;
+    static constexpr int G = L / 16;                         // threads per line
+    static constexpr int THREADS = (G >= 128) ? G : 128;
+    static constexpr int LPC = THREADS / G;                  // lines per CTA
+    static constexpr int SMEM = LPC * LinePlan<L>::PADDED * (int)sizeof(cpx);
+    // JAC parks the first product (-u * dvortdx) in shared memory while v and dvortdy are transformed
+    static constexpr int SMEM_JAC = SMEM + LPC * L * (int)sizeof(cpx);
+    static constexpr int MINB = (THREADS >= 512) ? 1 : (THREADS >= 256) ? 2 : 4;
+};
+
+// exp(-2 pi i q / 32), q = 0..15
+__device__ __forceinline__ cpx w32(int q)
+{
+    const float C[16] = {1.f, 0.98078528040323044913f, XFB_C16, 0.83146961230254523708f, XFB_C8, 0.55557023301960222474f,
+                         XFB_S16, 0.19509032201612826785f, 0.f, -0.19509032201612826785f, -XFB_S16,
+                         -0.55557023301960222474f, -XFB_C8, -0.83146961230254523708f, -XFB_C16, -0.98078528040323044913f};
+    const float S[16] = {0.f, -0.19509032201612826785f, -XFB_S16, -0.55557023301960222474f, -XFB_C8,
+                         -0.83146961230254523708f, -XFB_C16, -0.98078528040323044913f, -1.f, -0.98078528040323044913f,
+                         -XFB_C16, -0.83146961230254523708f, -XFB_C8, -0.55557023301960222474f, -XFB_S16,
+                         -0.19509032201612826785f};
+    return mk(C[q], S[q]);
+}
+
+// half-spectrum line X[0..L] -> physical pairs: on return v[q] = (x[2m+1], x[2m]) * 1 (unscaled,
+// swapped), m = t + q*G.  wt = exp(-2 pi i t / NY).
+template <int NY>
+__device__ __forceinline__ void c2r_line(cpx (&v)[16], const cpx *__restrict__ X, cpx *sm, int t, cpx wt,
+                                         const LineTw<NY / 2> &tw)
+{
+    constexpr int L = NY / 2, G = L / 16;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        cpx a[8], b[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = t + (8 * h + e) * G;
+            a[e] = __ldg(X + k);
+            b[e] = __ldg(X + (L - k));
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int q = 8 * h + e;
+            const int k = t + q * G;
+            cpx A = a[e], B = cconj(b[e]);
+            if (k == 0) { A.y = 0.f; B.y = 0.f; }      // c2r ignores Im of the DC and Nyquist bins
+            const cpx E = cadd(A, B), D = csub(A, B);
+            const cpx wk = cconj((q == 0) ? wt : cmul(wt, w32(q)));   // exp(+2 pi i k / NY)
+            const cpx O = cmul(D, wk);
+            // Z = E + i O ; swapped for the inverse transform
+            v[q] = mk(E.y + O.x, E.x - O.y);
+        }
+    }
+    line_fft<L, 1>(v, sm, t, 0, tw);
+}
+
+// physical pairs v[q] = (x[2m], x[2m+1]) -> half-spectrum line written to Xout[0..L] (+ zeroed pad)
+template <int NY>
+__device__ __forceinline__ void r2c_line(cpx (&v)[16], cpx *__restrict__ Xout, int pitch, cpx *sm, int t, cpx wt,
+                                         const LineTw<NY / 2> &tw)
+{
+    constexpr int L = NY / 2, G = L / 16;
+    line_fft<L, 1>(v, sm, t, 0, tw);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) sm[padpos(t + q * G)] = v[q];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int k = t + q * G;
+        const cpx Zk = v[q];
+        const cpx Zm = cconj(sm[padpos((L - k) & (L - 1))]);
+        const cpx E = mk(0.5f * (Zk.x + Zm.x), 0.5f * (Zk.y + Zm.y));
+        const cpx D = mk(0.5f * (Zk.x - Zm.x), 0.5f * (Zk.y - Zm.y));
+        const cpx wk = (q == 0) ? wt : cmul(wt, w32(q));           // exp(-2 pi i k / NY)
+        const cpx O = cmul(mul_negi(D), wk);
+        Xout[k] = cadd(E, O);
+        if (k == 0) Xout[L] = mk(Zk.x - Zk.y, 0.f);
+    }
+    if (t >= 1 && t < pitch - L) Xout[L + t] = mk(0.f, 0.f);
+}
+
+template <int NY, int MODE>
+__global__ void __launch_bounds__(RowCfg<NY>::THREADS, RowCfg<NY>::MINB)
+row_kernel(const RowParams p)
+{
+    typedef RowCfg<NY> C;
+    constexpr int L = C::L, G = C::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane_line = threadIdx.x / G;
+    const int t = threadIdx.x % G;
+    cpx *sm = reinterpret_cast<cpx *>(smem_raw) + (size_t)lane_line * LinePlan<L>::PADDED;
+    int row = blockIdx.x * C::LPC + lane_line;
+    const bool live = row < p.nrows;
+    if (!live) row = p.nrows - 1;
+
+    LineTw<L> tw;
+    tw.init(p.tw, p.twn, t);
+    const cpx wt = __ldg(p.tw + (size_t)t * (p.twn / NY));
+
+    cpx v[16];
+    if (MODE == ROW_R2C) {
+        const float2 *x = reinterpret_cast<const float2 *>(p.real_in + (size_t)row * NY);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = __ldg(x + t + q * G);
+        cpx *out = p.spec_out + (size_t)row * p.pitch;
+        if (live) r2c_line<NY>(v, out, p.pitch, sm, t, wt, tw);
+        else r2c_line<NY>(v, out, 0, sm, t, wt, tw);   // clamped duplicate row rewrites identical values
+    } else if (MODE == ROW_C2R) {
+        c2r_line<NY>(v, p.spec_in[0] + (size_t)row * p.pitch, sm, t, wt, tw);
+        float2 *x = reinterpret_cast<float2 *>(p.real_out + (size_t)row * NY);
+        const float s = p.negate ? -p.scale : p.scale;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) x[t + q * G] = mk(v[q].y * s, v[q].x * s);
+    } else {
+        const size_t off = (size_t)row * p.pitch;
+        cpx *park = reinterpret_cast<cpx *>(smem_raw) + (size_t)C::LPC * LinePlan<L>::PADDED + (size_t)lane_line * L;
+        cpx J[16];
+        // a = c2r(T_u)/GRIDS = -u ; J1 = (-u) * dvortdx                      (main.cpp:200-201,154,226)
+        c2r_line<NY>(v, p.spec_in[2] + off, sm, t, wt, tw);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) J[q] = mk(v[q].y * p.scale, v[q].x * p.scale);
+        c2r_line<NY>(v, p.spec_in[0] + off, sm, t, wt, tw);
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            park[q * G + t] = mk(J[q].x * (v[q].y * p.scale), J[q].y * (v[q].x * p.scale));
+        // v, dvortdy ; J = J1 - v * dvortdy                                  (main.cpp:214,168,226)
+        c2r_line<NY>(v, p.spec_in[3] + off, sm, t, wt, tw);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) J[q] = mk(v[q].y * p.scale, v[q].x * p.scale);
+        c2r_line<NY>(v, p.spec_in[1] + off, sm, t, wt, tw);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const cpx j1 = park[q * G + t];
+            J[q] = mk(j1.x - J[q].x * (v[q].y * p.scale), j1.y - J[q].y * (v[q].x * p.scale));
+        }
+        if (p.real_in != nullptr) {
+            const float2 *s = reinterpret_cast<const float2 *>(p.real_in + (size_t)row * NY);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float2 sv = __ldg(s + t + q * G);
+                J[q] = mk(J[q].x + sv.x, J[q].y + sv.y);
+            }
+        }
+        r2c_line<NY>(J, p.spec_out + off, live ? p.pitch : 0, sm, t, wt, tw);
+    }
+}
+
+}  // namespace xfb
