@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- RK4 grid-point.steps/s of the pseudospectral barotropic step on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 8192] [--impl xfb|reference]
+
+One "step" is one RK4 step (4 tendency evaluations = 20 2-D FFTs in the reference) of the elliptic
+vortex (reference generator makefield-elliptic-vortex.cpp) on a GRID x GRID doubly periodic domain.
+N > 1 (launched by torchrun, one rank per GPU): independent ensemble members, one per GPU, no
+data-path communication ("scaling": "weak"); the slab-decomposed single-field path is reported by
+the slab bench.
+
+Output: ONE JSON line on rank 0 (keys documented in DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "rk4_grid_point_steps_per_s"
+UNIT = "grid-pt*steps/s"
+ALGO_BYTES_PER_PT_STEP = 240.0      # 4 stages x (40 B K-COL + 20 B K-ROW)
+ALGO_BYTES_COL = 40.0               # per grid point per K-COL launch
+ALGO_BYTES_ROW = 20.0               # per grid point per K-ROW launch
+
+
+def dt_for(n: int) -> float:
+    """RK4 advective limit for the elliptic vortex (|U|max = 83 m/s): 0.6 * 2.83/(k_max |U|), SURVEY 8(d)"""
+    if n <= 1024:
+        return 3.0
+    kmax = 0.943 * np.pi * n / 600000.0
+    return float(np.float32(0.6 * 2.83 / (kmax * 83.0)))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons with NVML every 100 ms while the timed region runs"""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference leg (oracle/_ref = the unmodified reference main.cpp built against the FFT shim)
+# --------------------------------------------------------------------------------------------------
+
+def run_reference_steps(n: int, dt: float, steps_a: int, steps_b: int, threads: int):
+    """Times the UNMODIFIED reference binary for two run lengths and differences them
+    (start-up, table build and the step-0 record dump cancel).  Returns seconds per step."""
+    from oracle import build_oracle
+    import fields
+    exe = build_oracle.build_reference(n, programs=("main",)).get("main")
+    if exe is None:
+        return None, "no prebuilt reference binary for this grid"
+    v0 = fields.elliptic(n)
+    times = []
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "input"))
+        os.makedirs(os.path.join(d, "output"))
+        v0.tofile(os.path.join(d, "input", "initial_vorticity.bin"))
+        for steps in (steps_a, steps_b):
+            env = dict(os.environ, XFB_SHIM_THREADS=str(threads), XFB_DT=repr(float(dt)),
+                       XFB_TOTAL_STEPS=str(steps), XFB_RECORD_STEP=str(10 ** 9))
+            t0 = time.perf_counter()
+            subprocess.run([exe], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+            times.append(time.perf_counter() - t0)
+    return (times[1] - times[0]) / (steps_b - steps_a), None
+
+
+def cpu_baseline(sample_n: int, nsteps: int):
+    threads = os.cpu_count() or 1
+    sec, err = run_reference_steps(sample_n, dt_for(sample_n), 1, 1 + nsteps, threads)
+    if sec is None or sec <= 0:
+        return {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": err or "failed"}
+    return {
+        "value": sample_n * sample_n / sec, "unit": UNIT, "cores": threads, "kind": "reference",
+        "sample": (f"unmodified reference main.cpp + fftw3f-equivalent shim (FFT rows/columns on {threads} OpenMP "
+                   f"threads, pointwise loops single-threaded as in the reference), elliptic {sample_n}^2, "
+                   f"(T({1 + nsteps} steps) - T(1 step))/{nsteps}"),
+    }
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU path on this box's host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_n = args.ref_grid
+    threads = os.cpu_count() or 1
+    sec, err = run_reference_steps(sample_n, dt_for(sample_n), max(1, args.warmup), max(1, args.warmup) + args.steps, threads)
+    if sec is None:
+        print(json.dumps({"impl": "reference", "unavailable": err}))
+        return
+    val = sample_n * sample_n / sec
+    sample = (f"unmodified reference main.cpp (oracle/_ref) + fftw3f-equivalent shim, {threads} OpenMP threads in the "
+              f"FFTs, each step = one RK4 step of the elliptic vortex at {sample_n}^2 (bounded sample of the "
+              f"{args.grid}^2 workload), T({args.warmup}+{args.steps}) - T({args.warmup}) differenced")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"elliptic vortex {args.grid}^2 RK4 (reference arm sample {sample_n}^2)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+
+def gpu_arm(args):
+    import torch
+    import fields
+    import xlab_fftbarotropic_b200 as xfb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.grid
+    dt = dt_for(n)
+    G = n * n
+    b = xfb.Backend(n, batch=args.members, device=local_rank)
+    stream = torch.cuda.ExternalStream(b.stream, device=local_rank)
+
+    # synthetic input, resident in HBM before the timed region
+    v0 = fields.elliptic(n)
+    host_in = torch.from_numpy(v0).pin_memory()
+    host_out = torch.empty((n, n), dtype=torch.float32).pin_memory()
+    dev_in = host_in.to(f"cuda:{local_rank}")
+    torch.cuda.synchronize()
+    for m in range(args.members):
+        b.set_vorticity(int(dev_in.data_ptr()), member=m)
+    b.sync()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----------------------------------------------------
+    b.step(args.warmup, dt)
+    b.sync()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    l0 = b.launch_count
+    b.profile(True)
+    barrier()
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        b.step(args.steps, dt)
+        e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    prof = b.profile_read()
+    b.profile(False)
+    launches = b.launch_count - l0
+    if dist is not None:
+        t = torch.tensor([ms], device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    units = float(G) * args.members * world * args.steps
+    value = units / (ms * 1e-3)
+
+    # sanity: the state must still be finite (a CFL blow-up would make the number meaningless)
+    z = b.get_spectrum(0)
+    finite = bool(np.isfinite(z.view(np.float32)).all())
+
+    # ---- end to end through the C ABI with host buffers ("e2e") ---------------------------------
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    hin, hout = int(host_in.data_ptr()), int(host_out.data_ptr())
+    for _ in range(2):
+        b.set_vorticity(hin, member=0)
+        b.step(1, dt)
+        b._ck(b._L.xfb_get_field(b._h, 0, xfb.capi.VORT, hout))
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            for m in range(args.members):
+                b.set_vorticity(hin, member=m)            # H2D of this step's input (pinned)
+            b.step(1, dt)
+            for m in range(args.members):
+                b._ck(b._L.xfb_get_field(b._h, m, xfb.capi.VORT, hout))   # D2H of the step's result
+        e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_e2e], device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = float(G) * args.members * world * e2e_steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    col_avg = prof["col_ms"] / max(1, prof["col_launches"])
+    row_avg = prof["row_ms"] / max(1, prof["row_launches"])
+    pts = float(G) * args.members
+    col_gbs = ALGO_BYTES_COL * pts / (col_avg * 1e-3) / 1e9 if col_avg > 0 else 0.0
+    row_gbs = ALGO_BYTES_ROW * pts / (row_avg * 1e-3) / 1e9 if row_avg > 0 else 0.0
+    dominant = "col" if prof["col_ms"] >= prof["row_ms"] else "row"
+    achieved = col_gbs if dominant == "col" else row_gbs
+    step_gbs = ALGO_BYTES_PER_PT_STEP * value / world / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "kernel": "col_kernel<COL_STEP>" if dominant == "col" else "row_kernel<ROW_JAC>",
+        "peak_source": peak_src,
+        "kernels": {
+            "col_step": {"avg_ms": col_avg, "launches": prof["col_launches"], "algo_bytes_per_pt": ALGO_BYTES_COL,
+                         "gbs": col_gbs, "frac": col_gbs / peak},
+            "row_jac": {"avg_ms": row_avg, "launches": prof["row_launches"], "algo_bytes_per_pt": ALGO_BYTES_ROW,
+                        "gbs": row_gbs, "frac": row_gbs / peak},
+        },
+        "whole_step": {"algo_bytes_per_pt_step": ALGO_BYTES_PER_PT_STEP, "gbs": step_gbs, "frac": step_gbs / peak},
+    }
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.ref_grid, args.cpu_steps)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"elliptic vortex {n}^2 RK4 step, dt={dt:g}s, {args.members} member(s) per GPU"
+                        + (f", {world} GPUs x independent members (ensemble sharding)" if world > 1 else ""),
+            "grid": n, "members_per_gpu": args.members, "dt": dt,
+            "l2": "working set (8 spectral arrays, %.1f GB) is larger than the 126 MB L2" % (8 * 8 * (n // 2 + 4) * n * args.members / 1e9),
+            "state_finite": finite,
+        },
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * G * args.members,
+                "d2h_bytes_per_step": 4 * G * args.members, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+        "roofline": roofline,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="xfb", choices=["xfb", "reference"])
+    ap.add_argument("--grid", type=int, default=8192)
+    ap.add_argument("--members", type=int, default=1, help="ensemble members per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--ref-grid", type=int, default=2048, help="grid of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -109,6 +109,11 @@ int xfb_invert_pres(xfb_handle h, const float *psi, float *pres, size_t ref_x, s
 long long xfb_launch_count(xfb_handle h);
 /* cudaStream_t of the handle, as void* (for event timing by the caller) */
 void *xfb_stream(xfb_handle h);
+/* per-kernel CUDA-event timing of the stepper's two kernels (K-ROW = ROW_JAC, K-COL = COL_STEP):
+ * xfb_profile(h, 1) resets the counters and brackets every stepper launch with events on the
+ * handle's stream; xfb_profile_read synchronises and returns summed milliseconds and launch counts. */
+int xfb_profile(xfb_handle h, int enable);
+int xfb_profile_read(xfb_handle h, double *row_ms, long long *row_launches, double *col_ms, long long *col_launches);
 /* 1 if (nx, ny) is served by the fused power-of-two kernels, 2 if by the generic mixed-radix
  * path, 0 if unsupported */
 int xfb_size_supported(int nx, int ny);

@@ -174,7 +174,7 @@ def keff_from_hist(nbins, cmin, cmax, kappa, area, g2):
 
 def run_reference_generator(name: str, n: int, workdir: str | None = None) -> np.ndarray:
     """Run the UNMODIFIED reference generator binary (built here; prebuilt on the GPU box)."""
-    exe = build_oracle.build_reference(n, 3.0, 1200, 100, programs=(name,)).get(name)
+    exe = build_oracle.build_reference(n, programs=(name,)).get(name)
     if exe is None:
         raise FileNotFoundError(f"no reference binary for {name} at n={n}")
     with tempfile.TemporaryDirectory(dir=workdir) as d:
@@ -186,15 +186,16 @@ def run_reference_generator(name: str, n: int, workdir: str | None = None) -> np
 def run_reference_main(vort0: np.ndarray, n: int, dt: float, steps: int, record: int, env_threads: int = 1,
                        program: str = "main") -> dict:
     """Run the UNMODIFIED reference main.cpp for `steps` steps; returns {(kind, step): field}."""
-    exe = build_oracle.build_reference(n, dt, steps, record, programs=(program,)).get(program)
+    exe = build_oracle.build_reference(n, programs=(program,)).get(program)
     if exe is None:
-        raise FileNotFoundError(f"no reference binary for n={n} dt={dt} steps={steps} record={record}")
+        raise FileNotFoundError(f"no reference binary for n={n}")
     out = {}
     with tempfile.TemporaryDirectory() as d:
         os.makedirs(os.path.join(d, "input"))
         os.makedirs(os.path.join(d, "output"))
         np.ascontiguousarray(vort0, dtype="<f4").tofile(os.path.join(d, "input", "initial_vorticity.bin"))
-        env = dict(os.environ, XFB_SHIM_THREADS=str(env_threads))
+        env = dict(os.environ, XFB_SHIM_THREADS=str(env_threads), XFB_DT=repr(float(dt)),
+                   XFB_TOTAL_STEPS=str(int(steps)), XFB_RECORD_STEP=str(int(record)))
         subprocess.run([exe], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
         for line in open(os.path.join(d, "log")):
             path = line.strip()

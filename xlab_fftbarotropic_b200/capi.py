@@ -20,7 +20,7 @@ SYMBOLS = [
     "xfb_last_error", "xfb_create", "xfb_destroy", "xfb_sync", "xfb_gradx", "xfb_grady", "xfb_laplacian",
     "xfb_invert_laplacian", "xfb_dealias", "xfb_get_table", "xfb_r2c", "xfb_c2r", "xfb_set_vorticity",
     "xfb_set_spectrum", "xfb_get_spectrum", "xfb_set_source", "xfb_step", "xfb_get_field", "xfb_get_keff_hist",
-    "xfb_invert_pres", "xfb_launch_count", "xfb_stream", "xfb_size_supported",
+    "xfb_invert_pres", "xfb_launch_count", "xfb_stream", "xfb_size_supported", "xfb_profile", "xfb_profile_read",
 ]
 
 _lib = None
@@ -59,6 +59,9 @@ def load():
     L.xfb_stream.restype = vp
     L.xfb_stream.argtypes = [vp]
     L.xfb_size_supported.argtypes = [ci, ci]
+    L.xfb_profile.argtypes = [vp, ci]
+    L.xfb_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_longlong)]
     _lib = L
     return L
 
@@ -178,6 +181,16 @@ class Backend:
         out = np.empty((self.nx, self.ny), np.float32)
         self._ck(self._L.xfb_invert_pres(self._h, _ptr(psi), _ptr(out), ref_x, ref_y, rho, f))
         return out
+
+    def profile(self, enable=True):
+        self._ck(self._L.xfb_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> dict(row_ms, row_launches, col_ms, col_launches) summed since profile(True)"""
+        rm, cm = C.c_double(), C.c_double()
+        rl, cl = C.c_longlong(), C.c_longlong()
+        self._ck(self._L.xfb_profile_read(self._h, C.byref(rm), C.byref(rl), C.byref(cm), C.byref(cl)))
+        return {"row_ms": rm.value, "row_launches": rl.value, "col_ms": cm.value, "col_launches": cl.value}
 
     @property
     def launch_count(self):

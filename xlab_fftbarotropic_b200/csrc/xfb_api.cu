@@ -66,7 +66,21 @@ struct xfb_handle_s {
     cpx *spec_a, *spec_b;      // padded layout
     float *ref_a, *ref_b;      // reference layout half spectra (2*hgrids floats)
     long long launches;
+    // optional per-kernel timing (xfb_profile)
+    bool profiling;
+    std::vector<cudaEvent_t> *ev_row, *ev_col;   // pairs (begin, end)
+    size_t ev_row_used, ev_col_used;
 };
+
+static cudaEvent_t next_event(std::vector<cudaEvent_t> *pool, size_t &used)
+{
+    if (used == pool->size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        pool->push_back(e);
+    }
+    return (*pool)[used++];
+}
 
 static int dev_alloc(void **p, size_t bytes)
 {
@@ -248,6 +262,11 @@ extern "C" int xfb_destroy(xfb_handle h)
                     h->t[3], h->src, h->real_a, h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (auto pool : {h->ev_row, h->ev_col})
+        if (pool) {
+            for (cudaEvent_t e : *pool) cudaEventDestroy(e);
+            delete pool;
+        }
     cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -258,6 +277,39 @@ extern "C" int xfb_sync(xfb_handle h)
     if (!h) return fail(XFB_E_ARG, "null handle");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int xfb_profile(xfb_handle h, int enable)
+{
+    if (!h) return fail(XFB_E_ARG, "null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (!h->ev_row) h->ev_row = new std::vector<cudaEvent_t>();
+    if (!h->ev_col) h->ev_col = new std::vector<cudaEvent_t>();
+    h->ev_row_used = h->ev_col_used = 0;
+    h->profiling = enable != 0;
+    return 0;
+}
+
+extern "C" int xfb_profile_read(xfb_handle h, double *row_ms, long long *row_launches, double *col_ms, long long *col_launches)
+{
+    if (!h || !row_ms || !row_launches || !col_ms || !col_launches) return fail(XFB_E_ARG, "null argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    *row_ms = *col_ms = 0.0;
+    *row_launches = (long long)(h->ev_row_used / 2);
+    *col_launches = (long long)(h->ev_col_used / 2);
+    for (size_t i = 0; i + 1 < h->ev_row_used; i += 2) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, (*h->ev_row)[i], (*h->ev_row)[i + 1]));
+        *row_ms += ms;
+    }
+    for (size_t i = 0; i + 1 < h->ev_col_used; i += 2) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, (*h->ev_col)[i], (*h->ev_col)[i + 1]));
+        *col_ms += ms;
+    }
     return 0;
 }
 
@@ -478,10 +530,16 @@ extern "C" int xfb_step(xfb_handle h, int nsteps, float dt)
     }
     for (int s = 0; s < nsteps; ++s) {
         for (int k = 1; k <= 4; ++k) {
+            if (h->profiling) cudaEventRecord(next_event(h->ev_row, h->ev_row_used), h->stream);
             CKL(h, launch_row(h->ny, ROW_JAC, r, h->stream));
+            if (h->profiling) {
+                cudaEventRecord(next_event(h->ev_row, h->ev_row_used), h->stream);
+                cudaEventRecord(next_event(h->ev_col, h->ev_col_used), h->stream);
+            }
             c.stage = k;
             c.dt_stage = (k == 3) ? dt : dt / 2.0f;          // main.cpp:296,299,302
             CKL(h, launch_col(h->nx, COL_STEP, c, h->batch, h->stream));
+            if (h->profiling) cudaEventRecord(next_event(h->ev_col, h->ev_col_used), h->stream);
         }
     }
     return 0;
