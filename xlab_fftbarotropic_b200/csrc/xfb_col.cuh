@@ -35,6 +35,7 @@ struct ColParams {
     long long member_stride;   // complex elements between ensemble members
     int ny;               // for the mask reflection nothing is needed in y; kept for clarity
     double mask_kd;       // generalized_wavenumber_square (fftwfop.cpp:57), as stored in float
+    int mask_kd_i;        // the same as an integer (exact for every supported size)
     float nu;
     float dt;             // full step
     float dt_stage;       // dt/2, dt/2, dt for stages 1..3
@@ -45,10 +46,11 @@ template <int NX, int W>
 struct ColCfg {
     static constexpr int G = NX / 16;
     static constexpr int VT = G * W;                          // butterfly threads per tile
-    static constexpr int NIT = (VT >= 64) ? 2 : 1;
-    static constexpr int THREADS = VT / NIT;
+    static constexpr int THREADS = (VT > 512) ? 512 : VT;
+    static constexpr int NIT = VT / THREADS;                  // butterflies per thread per pass
     static constexpr int SMEM = LinePlan<NX>::PADDED * W * (int)sizeof(cpx);
-    static_assert(THREADS <= 1024 && THREADS >= 16, "bad column tile");
+    static constexpr int MINB = (THREADS <= 128) ? 4 : (THREADS <= 256) ? 2 : 1;
+    static_assert(THREADS >= 16 && NIT <= 2, "bad column tile");
 };
 
 // -(kx^2 + ky^2) narrowed to float, summed in float64 like pow(float,2)+pow(float,2) (fftwfop.cpp:42-45)
@@ -79,7 +81,7 @@ __device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&
 }
 
 template <int NX, int W, int MODE>
-__global__ void __launch_bounds__(ColCfg<NX, W>::THREADS, (ColCfg<NX, W>::THREADS <= 256) ? 2 : 1)
+__global__ void __launch_bounds__(ColCfg<NX, W>::THREADS, ColCfg<NX, W>::MINB)
 col_kernel(const ColParams p)
 {
     typedef ColCfg<NX, W> C;
@@ -101,6 +103,9 @@ col_kernel(const ColParams p)
     }
 
     cpx v[NIT][16];
+    // with one butterfly per thread the new stage state stays in registers for the four products
+    constexpr bool KEEP = (NIT == 1) && (MODE == COL_STEP);
+    cpx zkeep[KEEP ? 16 : 1];
 
     // ------------------------------------------------------------------ forward + epilogue
     if (MODE == COL_FWD || MODE == COL_STEP) {
@@ -114,7 +119,8 @@ col_kernel(const ColParams p)
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             const int j = j0 + c[it];
-            const double ky2 = p.ky2[j];
+            const float kyv = __ldg(p.ky + j);
+            const float ky2 = kyv * kyv;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const int i = t[it] + k * G;
@@ -125,13 +131,16 @@ col_kernel(const ColParams p)
                 } else {
                     const cpx z0v = p.z0[e];
                     const cpx zkv = (p.stage == 1) ? z0v : p.zk[e];
-                    const float lap = lap_coe(p.kx2[i], ky2);
+                    // fused path: -(kx^2 + ky^2) in float32 (<= 1 ulp from the reference's float64 sum;
+                    // the operator tier, xfb_laplacian, keeps the exact expression)
+                    const float kxv = __ldg(p.kx + i);
+                    const float lap = -fmaf(kxv, kxv, ky2);
                     // dvortdt_c += (vort_c * laplacian_coe) * NU
                     const float tx = __fadd_rn(X.x, __fmul_rn(__fmul_rn(zkv.x, lap), p.nu));
                     const float ty = __fadd_rn(X.y, __fmul_rn(__fmul_rn(zkv.y, lap), p.nu));
                     // dealiasing mask: (i^2 + j^2 >= kd) ? 0 : 1 with i reflected above NX/2
-                    const long long ii = (i <= NX / 2) ? i : NX - i;
-                    const float m = ((double)(ii * ii + (long long)j * j) >= p.mask_kd) ? 0.0f : 1.0f;
+                    const int ii = (i <= NX / 2) ? i : NX - i;
+                    const float m = (ii * ii + j * j >= p.mask_kd_i) ? 0.0f : 1.0f;
                     const float rx = __fmul_rn(tx, m), ry = __fmul_rn(ty, m);
                     cpx zn;
                     if (p.stage == 4) {
@@ -152,6 +161,7 @@ col_kernel(const ColParams p)
                         zn.y = __fadd_rn(z0v.y, __fmul_rn(ry, p.dt_stage));
                         p.zk[e] = zn;
                     }
+                    if (KEEP) v[it][k] = zn;
                 }
             }
         }
@@ -176,28 +186,33 @@ col_kernel(const ColParams p)
 
     // ------------------------------------------------------------------ prologue + 4 inverse
     if (MODE == COL_STEP || MODE == COL_PRO) {
-        // the state this thread just wrote (stage 4 / PRO: z0, else zk) is re-read from L1/L2
+        // the state this thread just wrote (stage 4 / PRO: z0, else zk): kept in registers (KEEP) or
+        // re-read from L1/L2
         const cpx *zsrc = (MODE == COL_PRO || p.stage == 4) ? p.z0 : p.zk;
+        if (KEEP) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) zkeep[k] = v[0][k];
+        }
 #pragma unroll 1
         for (int f = 0; f < 4; ++f) {
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int j = j0 + c[it];
                 const float ky = __ldg(p.ky + j);
-                const double ky2 = __ldg(p.ky2 + j);
+                const float ky2 = ky * ky;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const int i = t[it] + k * G;
-                    cpx z = zsrc[moff + (size_t)i * p.pitch + j];
+                    const cpx z = KEEP ? zkeep[k] : zsrc[moff + (size_t)i * p.pitch + j];
+                    const float kx = __ldg(p.kx + i);
+                    // f = 0: i kx Z, 1: i ky Z, 2: i ky Psi (u before negation), 3: i kx Psi (v);
+                    // Psi = Z / -(kx^2+ky^2), (0,0) entry divides by 1                 (fftwfop.cpp:43,112-117)
+                    float kk = (f == 0 || f == 3) ? kx : ky;
                     if (f >= 2) {
-                        // psi_c = vort_c / laplacian_coe_inverse, (0,0) entry = 1      (fftwfop.cpp:43,112-117)
-                        const float li = (i == 0 && j == 0) ? 1.0f : lap_coe(__ldg(p.kx2 + i), ky2);
-                        z = mk(__fdiv_rn(z.x, li), __fdiv_rn(z.y, li));
+                        const float li = (i == 0 && j == 0) ? 1.0f : -fmaf(kx, kx, ky2);
+                        kk = __fdividef(kk, li);
                     }
-                    // f = 0: i kx Z, 1: i ky Z, 2: i ky Psi (u before negation), 3: i kx Psi (v)
-                    const float kk = (f == 0 || f == 3) ? __ldg(p.kx + i) : ky;
-                    const cpx g = mk(__fmul_rn(-z.y, kk), __fmul_rn(z.x, kk));
-                    v[it][k] = cswap(g);
+                    v[it][k] = mk(z.x * kk, -z.y * kk);       // swap(i kk z) = swap(-z.y kk, z.x kk)
                 }
             }
             col_fft<NX, W, NIT>(v, sm, t, c, tw);

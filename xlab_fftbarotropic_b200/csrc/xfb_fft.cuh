@@ -29,6 +29,15 @@ __device__ __forceinline__ cpx cswap(cpx a) { return mk(a.y, a.x); }
 __device__ __forceinline__ cpx mul_negi(cpx a) { return mk(a.y, -a.x); }   // a * (-i)
 __device__ __forceinline__ cpx mul_i(cpx a) { return mk(-a.y, a.x); }      // a * (+i)
 
+// Identity the compiler cannot see through.  The twiddle bases are per-thread constants for the whole
+// kernel; without this the compiler keeps all their powers (60+ registers) live across the five
+// transforms of a row/tile and spills.  Laundering the base at each use forces a cheap recomputation.
+__device__ __forceinline__ cpx launder(cpx w)
+{
+    asm volatile("" : "+f"(w.x), "+f"(w.y));
+    return w;
+}
+
 #define XFB_C8 0.70710678118654752440f
 #define XFB_C16 0.92387953251128675613f
 #define XFB_S16 0.38268343236508977173f
@@ -150,33 +159,63 @@ struct LineTw {
 
 // ---- pass pieces (composed by line_fft below and by the multi-iteration column kernel) ----
 
+// v[s] *= w1^s, s = 1..15.  Powers by a depth-4 product tree (w2, w4, w8 by squaring, the rest as
+// products of two of them), generated and applied in an order that keeps few of them live.
+__device__ __forceinline__ void apply_twiddles16(cpx (&v)[16], const cpx w1)
+{
+    const cpx w2 = cmul(w1, w1), w4 = cmul(w2, w2), w8 = cmul(w4, w4);
+    v[1] = cmul(v[1], w1);
+    v[2] = cmul(v[2], w2);
+    v[4] = cmul(v[4], w4);
+    v[8] = cmul(v[8], w8);
+    v[9] = cmul(v[9], cmul(w8, w1));
+    v[10] = cmul(v[10], cmul(w8, w2));
+    v[12] = cmul(v[12], cmul(w8, w4));
+    const cpx w3 = cmul(w2, w1);
+    v[3] = cmul(v[3], w3);
+    v[11] = cmul(v[11], cmul(w8, w3));
+    const cpx w5 = cmul(w4, w1);
+    v[5] = cmul(v[5], w5);
+    v[13] = cmul(v[13], cmul(w8, w5));
+    const cpx w6 = cmul(w4, w2);
+    v[6] = cmul(v[6], w6);
+    v[14] = cmul(v[14], cmul(w8, w6));
+    const cpx w7 = cmul(w4, w3);
+    v[7] = cmul(v[7], w7);
+    v[15] = cmul(v[15], cmul(w8, w7));
+}
+
 // radix-16 pass p: twiddle (p > 0) + butterfly
 template <int L>
 __device__ __forceinline__ void pass16_compute(cpx (&v)[16], const int p, const LineTw<L> &tw)
 {
-    if (p > 0) {
-        cpx w[16];
-        pow_chain16(tw.b[p], w);
-#pragma unroll
-        for (int s = 1; s < 16; ++s) v[s] = cmul(v[s], w[s]);
-    }
+    if (p > 0) apply_twiddles16(v, launder(tw.b[p]));
     dft16(v);
 }
 
-// Stockham scatter of pass-p results (ns = 16^p); element address = padpos(pos) * W + c
+// Stockham scatter of pass-p results (ns = 16^p); element address = padpos(pos) * W + c.
+// base % 16 + (s*ns) % 16 < 16 for every pass (ns = 1: base = 16 t; ns >= 16: s*ns % 16 = 0), so
+// padpos(base + s*ns) = padpos(base) + s*ns + (s*ns >> 4): constant offsets from one address.
 template <int W>
 __device__ __forceinline__ void exchange_write(const cpx (&v)[16], cpx *sm, const int t, const int c, const int ns)
 {
     const int base = (t / ns) * ns * 16 + (t % ns);
+    cpx *dst = sm + padpos(base) * W + c;
 #pragma unroll
-    for (int s = 0; s < 16; ++s) sm[padpos(base + s * ns) * W + c] = v[s];
+    for (int s = 0; s < 16; ++s) dst[(s * ns + ((s * ns) >> 4)) * W] = v[s];
 }
 
 template <int G, int W>
 __device__ __forceinline__ void exchange_read(cpx (&v)[16], const cpx *sm, const int t, const int c)
 {
+    if (G % 16 == 0) {
+        const cpx *src = sm + padpos(t) * W + c;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = sm[padpos(t + k * G) * W + c];
+        for (int k = 0; k < 16; ++k) v[k] = src[k * (G + G / 16) * W];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = sm[padpos(t + k * G) * W + c];
+    }
 }
 
 // remainder pass, radix r = REM (last pass): butterflies q = 0..16/r-1 at j = t + q*G use register
@@ -189,9 +228,10 @@ __device__ __forceinline__ void rem_pass(cpx (&v)[16], const LineTw<L> &tw)
         constexpr int r = (P::REM > 1) ? P::REM : 2, nb = 16 / r;
         const float CQ[8] = {1.f, XFB_C16, XFB_C8, XFB_S16, 0.f, -XFB_S16, -XFB_C8, -XFB_C16};
         const float SQ[8] = {0.f, -XFB_S16, -XFB_C8, -XFB_C16, -1.f, -XFB_C16, -XFB_C8, -XFB_S16};
+        const cpx wb = launder(tw.b[0]);
 #pragma unroll
         for (int q = 0; q < nb; ++q) {
-            const cpx w1 = (q == 0) ? tw.b[0] : cmul(tw.b[0], mk(CQ[q], SQ[q]));
+            const cpx w1 = (q == 0) ? wb : cmul(wb, mk(CQ[q], SQ[q]));
             if (r == 2) {
                 cpx a = v[q], b = cmul(v[q + nb], w1);
                 v[q] = cadd(a, b);

@@ -35,8 +35,9 @@ struct RowCfg {
     static constexpr int THREADS = (G >= 128) ? G : 128;
     static constexpr int LPC = THREADS / G;                  // lines per CTA
     static constexpr int SMEM = LPC * LinePlan<L>::PADDED * (int)sizeof(cpx);
-    // JAC parks the first product (-u * dvortdx) in shared memory while v and dvortdy are transformed
-    static constexpr int SMEM_JAC = SMEM + LPC * L * (int)sizeof(cpx);
+    // JAC parks -u (then -u * dvortdx) and v in shared memory between the four inverse transforms, so
+    // no physical-space field is live in registers across a transform
+    static constexpr int SMEM_JAC = SMEM + 2 * LPC * L * (int)sizeof(cpx);
     static constexpr int MINB = (THREADS >= 512) ? 1 : (THREADS >= 256) ? 2 : 4;
 };
 
@@ -56,18 +57,19 @@ __device__ __forceinline__ cpx w32(int q)
 // half-spectrum line X[0..L] -> physical pairs: on return v[q] = (x[2m+1], x[2m]) * 1 (unscaled,
 // swapped), m = t + q*G.  wt = exp(-2 pi i t / NY).
 template <int NY>
-__device__ __forceinline__ void c2r_line(cpx (&v)[16], const cpx *__restrict__ X, cpx *sm, int t, cpx wt,
+__device__ __forceinline__ void c2r_line(cpx (&v)[16], const cpx *X, cpx *sm, int t, cpx wt,
                                          const LineTw<NY / 2> &tw)
 {
     constexpr int L = NY / 2, G = L / 16;
+    wt = launder(wt);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         cpx a[8], b[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int k = t + (8 * h + e) * G;
-            a[e] = __ldg(X + k);
-            b[e] = __ldg(X + (L - k));
+            a[e] = X[k];
+            b[e] = X[L - k];
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -92,6 +94,7 @@ __device__ __forceinline__ void r2c_line(cpx (&v)[16], cpx *__restrict__ Xout, i
 {
     constexpr int L = NY / 2, G = L / 16;
     line_fft<L, 1>(v, sm, t, 0, tw);
+    wt = launder(wt);
 #pragma unroll
     for (int q = 0; q < 16; ++q) sm[padpos(t + q * G)] = v[q];
     __syncthreads();
@@ -144,25 +147,28 @@ row_kernel(const RowParams p)
         for (int q = 0; q < 16; ++q) x[t + q * G] = mk(v[q].y * s, v[q].x * s);
     } else {
         const size_t off = (size_t)row * p.pitch;
-        cpx *park = reinterpret_cast<cpx *>(smem_raw) + (size_t)C::LPC * LinePlan<L>::PADDED + (size_t)lane_line * L;
-        cpx J[16];
+        cpx *park0 = reinterpret_cast<cpx *>(smem_raw) + (size_t)C::LPC * LinePlan<L>::PADDED + (size_t)lane_line * (2 * L);
+        cpx *park1 = park0 + L;
         // a = c2r(T_u)/GRIDS = -u ; J1 = (-u) * dvortdx                      (main.cpp:200-201,154,226)
         c2r_line<NY>(v, p.spec_in[2] + off, sm, t, wt, tw);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) J[q] = mk(v[q].y * p.scale, v[q].x * p.scale);
+        for (int q = 0; q < 16; ++q) park0[q * G + t] = mk(v[q].y * p.scale, v[q].x * p.scale);
         c2r_line<NY>(v, p.spec_in[0] + off, sm, t, wt, tw);
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
-            park[q * G + t] = mk(J[q].x * (v[q].y * p.scale), J[q].y * (v[q].x * p.scale));
+        for (int q = 0; q < 16; ++q) {
+            const cpx a = park0[q * G + t];
+            park0[q * G + t] = mk(a.x * (v[q].y * p.scale), a.y * (v[q].x * p.scale));
+        }
         // v, dvortdy ; J = J1 - v * dvortdy                                  (main.cpp:214,168,226)
         c2r_line<NY>(v, p.spec_in[3] + off, sm, t, wt, tw);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) J[q] = mk(v[q].y * p.scale, v[q].x * p.scale);
+        for (int q = 0; q < 16; ++q) park1[q * G + t] = mk(v[q].y * p.scale, v[q].x * p.scale);
         c2r_line<NY>(v, p.spec_in[1] + off, sm, t, wt, tw);
+        cpx J[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            const cpx j1 = park[q * G + t];
-            J[q] = mk(j1.x - J[q].x * (v[q].y * p.scale), j1.y - J[q].y * (v[q].x * p.scale));
+            const cpx j1 = park0[q * G + t], vv = park1[q * G + t];
+            J[q] = mk(j1.x - vv.x * (v[q].y * p.scale), j1.y - vv.y * (v[q].x * p.scale));
         }
         if (p.real_in != nullptr) {
             const float2 *s = reinterpret_cast<const float2 *>(p.real_in + (size_t)row * NY);
