@@ -391,6 +391,7 @@ static void fill_col(xfb_handle h, ColParams &p)
     p.tw = h->tw; p.twn = h->twn; p.kx = h->kx; p.ky = h->ky; p.kx2 = h->kx2; p.ky2 = h->ky2;
     p.pitch = h->pitch; p.member_stride = (long long)h->hpad; p.ny = h->ny; p.mask_kd = h->mask_kd; p.nu = h->nu;
     p.mask_kd_i = (int)h->mask_kd;
+    p.kxscale = (acosf(-1.0f) * 2.0f) / h->lx;
 }
 
 // real [nx][ny] (device) -> padded spectrum (device), via `tmp` (padded)

@@ -36,6 +36,7 @@ struct ColParams {
     int ny;               // for the mask reflection nothing is needed in y; kept for clarity
     double mask_kd;       // generalized_wavenumber_square (fftwfop.cpp:57), as stored in float
     int mask_kd_i;        // the same as an integer (exact for every supported size)
+    float kxscale;        // TWOPI / Lx: fused path forms kx = (signed index) * kxscale in registers
     float nu;
     float dt;             // full step
     float dt_stage;       // dt/2, dt/2, dt for stages 1..3
@@ -55,6 +56,17 @@ struct ColCfg {
 
 // -(kx^2 + ky^2) narrowed to float, summed in float64 like pow(float,2)+pow(float,2) (fftwfop.cpp:42-45)
 __device__ __forceinline__ float lap_coe(const double kx2, const double ky2) { return (float)(-(kx2 + ky2)); }
+
+// signed x wavenumber index of row i = t + k*G (k compile-time): i for i <= NX/2 (Nyquist keeps +), else i - NX
+template <int NX>
+__device__ __forceinline__ int signed_row(const int t, const int k)
+{
+    constexpr int G = NX / 16;
+    const int i = t + k * G;
+    if (k < 8) return i;
+    if (k == 8) return (t == 0) ? i : i - NX;
+    return i - NX;
+}
 
 template <int NX, int W, int NIT>
 __device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&t)[NIT], const int (&c)[NIT],
@@ -115,53 +127,79 @@ col_kernel(const ColParams p)
 #pragma unroll
             for (int k = 0; k < 16; ++k) v[it][k] = __ldg(src + (size_t)(t[it] + k * G) * p.pitch);
         }
+        if (MODE == COL_STEP) {
+            // the epilogue operands of this tile: start them towards L2 now, they are needed after the
+            // forward transform (three passes from here)
+            for (int r = threadIdx.x; r < NX; r += C::THREADS) {
+                const size_t e = moff + (size_t)r * p.pitch + j0;
+                prefetch_l2(p.z0 + e);
+                if (p.stage != 1) {
+                    prefetch_l2(p.zk + e);
+                    prefetch_l2(p.acc + e);
+                }
+            }
+        }
         col_fft<NX, W, NIT>(v, sm, t, c, tw);
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
             const int j = j0 + c[it];
             const float kyv = __ldg(p.ky + j);
             const float ky2 = kyv * kyv;
+            const size_t e0 = moff + (size_t)t[it] * p.pitch + j;
+            if (MODE == COL_FWD) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int i = t[it] + k * G;
-                const size_t e = moff + (size_t)i * p.pitch + j;
-                const cpx X = v[it][k];
-                if (MODE == COL_FWD) {
-                    p.z0[e] = X;
-                } else {
-                    const cpx z0v = p.z0[e];
-                    const cpx zkv = (p.stage == 1) ? z0v : p.zk[e];
-                    // fused path: -(kx^2 + ky^2) in float32 (<= 1 ulp from the reference's float64 sum;
-                    // the operator tier, xfb_laplacian, keeps the exact expression)
-                    const float kxv = __ldg(p.kx + i);
-                    const float lap = -fmaf(kxv, kxv, ky2);
-                    // dvortdt_c += (vort_c * laplacian_coe) * NU
-                    const float tx = __fadd_rn(X.x, __fmul_rn(__fmul_rn(zkv.x, lap), p.nu));
-                    const float ty = __fadd_rn(X.y, __fmul_rn(__fmul_rn(zkv.y, lap), p.nu));
-                    // dealiasing mask: (i^2 + j^2 >= kd) ? 0 : 1 with i reflected above NX/2
-                    const int ii = (i <= NX / 2) ? i : NX - i;
-                    const float m = (ii * ii + j * j >= p.mask_kd_i) ? 0.0f : 1.0f;
-                    const float rx = __fmul_rn(tx, m), ry = __fmul_rn(ty, m);
-                    cpx zn;
-                    if (p.stage == 4) {
-                        const cpx a = p.acc[e];
-                        zn.x = __fadd_rn(z0v.x, __fdiv_rn(__fmul_rn(__fadd_rn(a.x, rx), p.dt), 6.0f));
-                        zn.y = __fadd_rn(z0v.y, __fdiv_rn(__fmul_rn(__fadd_rn(a.y, ry), p.dt), 6.0f));
-                        p.z0[e] = zn;
-                    } else {
-                        cpx an;
-                        if (p.stage == 1) {
-                            an = mk(rx, ry);
-                        } else {
-                            const cpx a = p.acc[e];
-                            an = mk(__fadd_rn(a.x, __fmul_rn(2.0f, rx)), __fadd_rn(a.y, __fmul_rn(2.0f, ry)));
+                for (int k = 0; k < 16; ++k) p.z0[e0 + (size_t)(k * G) * p.pitch] = v[it][k];
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    // operands of eight elements in flight at once
+                    cpx z0v[8], zkv[8], av[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) z0v[q] = p.z0[e0 + (size_t)((8 * h + q) * G) * p.pitch];
+                    if (p.stage != 1) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            zkv[q] = p.zk[e0 + (size_t)((8 * h + q) * G) * p.pitch];
+                            av[q] = p.acc[e0 + (size_t)((8 * h + q) * G) * p.pitch];
                         }
-                        p.acc[e] = an;
-                        zn.x = __fadd_rn(z0v.x, __fmul_rn(rx, p.dt_stage));
-                        zn.y = __fadd_rn(z0v.y, __fmul_rn(ry, p.dt_stage));
-                        p.zk[e] = zn;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { zkv[q] = z0v[q]; av[q] = mk(0.f, 0.f); }
                     }
-                    if (KEEP) v[it][k] = zn;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int k = 8 * h + q;
+                        const int i = t[it] + k * G;
+                        const size_t e = e0 + (size_t)(k * G) * p.pitch;
+                        const cpx X = v[it][k];
+                        // fused path: kx = (signed index) * TWOPI/Lx and -(kx^2 + ky^2) in float32 (<= 2 ulp
+                        // from the reference tables; the operator tier keeps the exact expressions)
+                        const float kxv = (float)signed_row<NX>(t[it], k) * p.kxscale;
+                        const float lap = -fmaf(kxv, kxv, ky2);
+                        // dvortdt_c += (vort_c * laplacian_coe) * NU
+                        const float tx = __fadd_rn(X.x, __fmul_rn(__fmul_rn(zkv[q].x, lap), p.nu));
+                        const float ty = __fadd_rn(X.y, __fmul_rn(__fmul_rn(zkv[q].y, lap), p.nu));
+                        // dealiasing mask: (i^2 + j^2 >= kd) ? 0 : 1 with i reflected above NX/2
+                        const int ii = (i <= NX / 2) ? i : NX - i;
+                        const float m = (ii * ii + j * j >= p.mask_kd_i) ? 0.0f : 1.0f;
+                        const float rx = __fmul_rn(tx, m), ry = __fmul_rn(ty, m);
+                        cpx zn;
+                        if (p.stage == 4) {
+                            zn.x = __fadd_rn(z0v[q].x, __fdiv_rn(__fmul_rn(__fadd_rn(av[q].x, rx), p.dt), 6.0f));
+                            zn.y = __fadd_rn(z0v[q].y, __fdiv_rn(__fmul_rn(__fadd_rn(av[q].y, ry), p.dt), 6.0f));
+                            p.z0[e] = zn;
+                        } else {
+                            // stage 1: acc = r1 ; stages 2,3: acc += 2 r
+                            const cpx an = (p.stage == 1) ? mk(rx, ry)
+                                                          : mk(__fadd_rn(av[q].x, __fmul_rn(2.0f, rx)),
+                                                               __fadd_rn(av[q].y, __fmul_rn(2.0f, ry)));
+                            p.acc[e] = an;
+                            zn.x = __fadd_rn(z0v[q].x, __fmul_rn(rx, p.dt_stage));
+                            zn.y = __fadd_rn(z0v[q].y, __fmul_rn(ry, p.dt_stage));
+                            p.zk[e] = zn;
+                        }
+                        if (KEEP) v[it][k] = zn;
+                    }
                 }
             }
         }
@@ -195,6 +233,14 @@ col_kernel(const ColParams p)
         }
 #pragma unroll 1
         for (int f = 0; f < 4; ++f) {
+            if (!KEEP) {
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    const cpx *src = zsrc + moff + (size_t)t[it] * p.pitch + j0 + c[it];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[it][k] = src[(size_t)(k * G) * p.pitch];
+                }
+            }
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int j = j0 + c[it];
@@ -203,8 +249,8 @@ col_kernel(const ColParams p)
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const int i = t[it] + k * G;
-                    const cpx z = KEEP ? zkeep[k] : zsrc[moff + (size_t)i * p.pitch + j];
-                    const float kx = __ldg(p.kx + i);
+                    const cpx z = KEEP ? zkeep[k] : v[it][k];
+                    const float kx = (float)signed_row<NX>(t[it], k) * p.kxscale;
                     // f = 0: i kx Z, 1: i ky Z, 2: i ky Psi (u before negation), 3: i kx Psi (v);
                     // Psi = Z / -(kx^2+ky^2), (0,0) entry divides by 1                 (fftwfop.cpp:43,112-117)
                     float kk = (f == 0 || f == 3) ? kx : ky;

@@ -38,6 +38,8 @@ __device__ __forceinline__ cpx launder(cpx w)
     return w;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
 #define XFB_C8 0.70710678118654752440f
 #define XFB_C16 0.92387953251128675613f
 #define XFB_S16 0.38268343236508977173f

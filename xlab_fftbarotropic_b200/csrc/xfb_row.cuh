@@ -148,27 +148,41 @@ row_kernel(const RowParams p)
     } else {
         const size_t off = (size_t)row * p.pitch;
         cpx *park0 = reinterpret_cast<cpx *>(smem_raw) + (size_t)C::LPC * LinePlan<L>::PADDED + (size_t)lane_line * (2 * L);
-        cpx *park1 = park0 + L;
-        // a = c2r(T_u)/GRIDS = -u ; J1 = (-u) * dvortdx                      (main.cpp:200-201,154,226)
-        c2r_line<NY>(v, p.spec_in[2] + off, sm, t, wt, tw);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) park0[q * G + t] = mk(v[q].y * p.scale, v[q].x * p.scale);
-        c2r_line<NY>(v, p.spec_in[0] + off, sm, t, wt, tw);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const cpx a = park0[q * G + t];
-            park0[q * G + t] = mk(a.x * (v[q].y * p.scale), a.y * (v[q].x * p.scale));
+        // pull the three lines that are not needed first into L2 while the first transform runs
+        {
+            constexpr int LINE_BYTES = (L + 1) * (int)sizeof(cpx);
+            for (int o = t * 128; o < LINE_BYTES; o += G * 128) {
+                prefetch_l2(reinterpret_cast<const char *>(p.spec_in[0] + off) + o);
+                prefetch_l2(reinterpret_cast<const char *>(p.spec_in[3] + off) + o);
+                prefetch_l2(reinterpret_cast<const char *>(p.spec_in[1] + off) + o);
+            }
         }
-        // v, dvortdy ; J = J1 - v * dvortdy                                  (main.cpp:214,168,226)
-        c2r_line<NY>(v, p.spec_in[3] + off, sm, t, wt, tw);
+        // One code path for the four inverse transforms (keeps the kernel inside the instruction cache):
+        //   f = 0: a = c2r(T_u)/GRIDS = -u      -> park0 = a              (main.cpp:200-201)
+        //   f = 1: dvortdx                      -> park0 = a * dvortdx    (main.cpp:154,226)
+        //   f = 2: v                            -> park1 = v              (main.cpp:214)
+        //   f = 3: dvortdy                      -> park1 = v * dvortdy    (main.cpp:168,226)
+#pragma unroll 1
+        for (int f = 0; f < 4; ++f) {
+            const int src_field = (f == 0) ? 2 : (f == 1) ? 0 : (f == 2) ? 3 : 1;
+            c2r_line<NY>(v, p.spec_in[src_field] + off, sm, t, wt, tw);
+            cpx *park = park0 + (f >> 1) * L;
+            if (f & 1) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) park1[q * G + t] = mk(v[q].y * p.scale, v[q].x * p.scale);
-        c2r_line<NY>(v, p.spec_in[1] + off, sm, t, wt, tw);
+                for (int q = 0; q < 16; ++q) {
+                    const cpx a = park[q * G + t];
+                    park[q * G + t] = mk(a.x * (v[q].y * p.scale), a.y * (v[q].x * p.scale));
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) park[q * G + t] = mk(v[q].y * p.scale, v[q].x * p.scale);
+            }
+        }
         cpx J[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            const cpx j1 = park0[q * G + t], vv = park1[q * G + t];
-            J[q] = mk(j1.x - vv.x * (v[q].y * p.scale), j1.y - vv.y * (v[q].x * p.scale));
+            const cpx j1 = park0[q * G + t], j2 = park0[L + q * G + t];
+            J[q] = mk(j1.x - j2.x, j1.y - j2.y);
         }
         if (p.real_in != nullptr) {
             const float2 *s = reinterpret_cast<const float2 *>(p.real_in + (size_t)row * NY);
