@@ -46,6 +46,7 @@ extern "C" const char *xfb_last_error(void) { return g_err; }
 // ------------------------------------------------------------------------------------------------
 struct xfb_handle_s {
     int nx, ny, hy, pitch, batch, device;
+    int tw_state;        // column tile width = tile-major layout of z0/zk/acc
     float lx, ly, nu;
     size_t grids, hgrids, hpad;   // per member: nx*ny, nx*(ny/2+1), nx*pitch
     cudaStream_t stream;
@@ -112,6 +113,7 @@ struct PwParams {
     const cpx *in;
     cpx *out;
     int nx, in_pitch, out_pitch, ncols;   // ncols columns are processed; the rest of out's pitch is zeroed
+    int in_tw, out_tw;                    // > 0: that side is in the stepper's tile-major layout, tile width tw
     const float *kx, *ky;
     const double *kx2, *ky2;
     double mask_kd;
@@ -125,8 +127,10 @@ __global__ void pointwise_kernel(const PwParams p)
     const long long total = (long long)p.nx * p.out_pitch;
     if (idx >= total) return;
     const int i = (int)(idx / p.out_pitch), j = (int)(idx % p.out_pitch);
-    if (j >= p.ncols) { p.out[idx] = mk(0.f, 0.f); return; }
-    const cpx z = p.in[(size_t)i * p.in_pitch + j];
+    const size_t oidx = p.out_tw ? ((size_t)(j / p.out_tw) * p.nx + i) * p.out_tw + (j % p.out_tw) : (size_t)idx;
+    if (j >= p.ncols) { p.out[oidx] = mk(0.f, 0.f); return; }
+    const cpx z = p.in_tw ? p.in[((size_t)(j / p.in_tw) * p.nx + i) * p.in_tw + (j % p.in_tw)]
+                          : p.in[(size_t)i * p.in_pitch + j];
     cpx r = z;
     switch (p.op) {
     case OP_GRADX: { const float k = p.kx[i]; r = mk(__fmul_rn(-z.y, k), __fmul_rn(z.x, k)); break; }
@@ -145,7 +149,7 @@ __global__ void pointwise_kernel(const PwParams p)
     }
     default: break;
     }
-    p.out[idx] = r;
+    p.out[oidx] = r;
 }
 
 // tables in the reference's H-sized form, for xfb_get_table (parity tests of fftwfop.cpp:40-68)
@@ -163,10 +167,12 @@ __global__ void table_kernel(float *out, int which, int nx, int hy, const double
     }
 }
 
-static int launch_pw(xfb_handle h, int op, const cpx *in, int in_pitch, cpx *out, int out_pitch, int ncols)
+static int launch_pw(xfb_handle h, int op, const cpx *in, int in_pitch, cpx *out, int out_pitch, int ncols,
+                     int in_tw = 0, int out_tw = 0)
 {
     PwParams p;
     p.in = in; p.out = out; p.nx = h->nx; p.in_pitch = in_pitch; p.out_pitch = out_pitch; p.ncols = ncols;
+    p.in_tw = in_tw; p.out_tw = out_tw;
     p.kx = h->kx; p.ky = h->ky; p.kx2 = h->kx2; p.ky2 = h->ky2; p.mask_kd = h->mask_kd; p.op = op;
     const long long total = (long long)h->nx * out_pitch;
     const int threads = 256;
@@ -200,6 +206,7 @@ extern "C" int xfb_create(xfb_handle *out, int nx, int ny, float lx, float ly, f
     memset(h, 0, sizeof(*h));
     h->nx = nx; h->ny = ny; h->hy = ny / 2 + 1; h->pitch = ny / 2 + 4; h->batch = batch; h->device = device;
     h->lx = lx; h->ly = ly; h->nu = nu;
+    h->tw_state = col_tile_width(nx);
     h->grids = (size_t)nx * ny; h->hgrids = (size_t)nx * h->hy; h->hpad = (size_t)nx * h->pitch;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 
@@ -391,6 +398,7 @@ static void fill_col(xfb_handle h, ColParams &p)
     p.tw = h->tw; p.twn = h->twn; p.kx = h->kx; p.ky = h->ky; p.kx2 = h->kx2; p.ky2 = h->ky2;
     p.pitch = h->pitch; p.member_stride = (long long)h->hpad; p.ny = h->ny; p.mask_kd = h->mask_kd; p.nu = h->nu;
     p.mask_kd_i = (int)h->mask_kd;
+    p.st_tile_stride = col_tile_width(h->nx); p.st_row_stride = h->pitch;      // row-major unless the stepper says otherwise
     p.kxscale = (acosf(-1.0f) * 2.0f) / h->lx;
 }
 
@@ -459,7 +467,9 @@ extern "C" int xfb_set_vorticity(xfb_handle h, int member, const float *vort)
     CK(cudaSetDevice(h->device));
     const void *din;
     if (stage_in(h, vort, h->real_a, sizeof(float) * h->grids, &din)) return XFB_E_CUDA;
-    if (fwd2d(h, (const float *)din, h->spec_a, h->z0 + (size_t)member * h->hpad)) return XFB_E_CUDA;
+    if (fwd2d(h, (const float *)din, h->spec_a, h->spec_b)) return XFB_E_CUDA;
+    if (launch_pw(h, OP_COPY, h->spec_b, h->pitch, h->z0 + (size_t)member * h->hpad, h->pitch, h->pitch, 0, h->tw_state))
+        return XFB_E_CUDA;
     h->have_state = true;
     h->tf_valid = false;
     if (!is_device_ptr(vort)) CK(cudaStreamSynchronize(h->stream));
@@ -473,7 +483,8 @@ extern "C" int xfb_set_spectrum(xfb_handle h, int member, const float *spec)
     CK(cudaSetDevice(h->device));
     const void *din;
     if (stage_in(h, spec, h->ref_a, sizeof(cpx) * h->hgrids, &din)) return XFB_E_CUDA;
-    if (launch_pw(h, OP_COPY, (const cpx *)din, h->hy, h->z0 + (size_t)member * h->hpad, h->pitch, h->hy)) return XFB_E_CUDA;
+    if (launch_pw(h, OP_COPY, (const cpx *)din, h->hy, h->z0 + (size_t)member * h->hpad, h->pitch, h->hy, 0, h->tw_state))
+        return XFB_E_CUDA;
     h->have_state = true;
     h->tf_valid = false;
     if (!is_device_ptr(spec)) CK(cudaStreamSynchronize(h->stream));
@@ -487,7 +498,8 @@ extern "C" int xfb_get_spectrum(xfb_handle h, int member, float *spec)
     if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_spectrum before xfb_set_vorticity");
     CK(cudaSetDevice(h->device));
     void *dout = stage_out_target(spec, h->ref_a);
-    if (launch_pw(h, OP_COPY, h->z0 + (size_t)member * h->hpad, h->pitch, (cpx *)dout, h->hy, h->hy)) return XFB_E_CUDA;
+    if (launch_pw(h, OP_COPY, h->z0 + (size_t)member * h->hpad, h->pitch, (cpx *)dout, h->hy, h->hy, h->tw_state, 0))
+        return XFB_E_CUDA;
     return stage_out(h, spec, dout, sizeof(cpx) * h->hgrids);
 }
 
@@ -520,6 +532,7 @@ extern "C" int xfb_step(xfb_handle h, int nsteps, float dt)
     CK(cudaSetDevice(h->device));
     ColParams c; fill_col(h, c);
     c.jint = h->jint; c.z0 = h->z0; c.zk = h->zk; c.acc = h->acc;
+    c.st_tile_stride = (long long)h->nx * h->tw_state; c.st_row_stride = h->tw_state;     // tile-major state
     for (int f = 0; f < 4; ++f) c.t_out[f] = h->t[f];
     c.dt = dt;
     RowParams r; fill_row(h, r, h->nx * h->batch);
@@ -552,26 +565,27 @@ static int derived_field(xfb_handle h, int member, int which, float *dout)
 {
     const cpx *z = h->z0 + (size_t)member * h->hpad;
     const float scale = 1.0f / (float)((double)h->nx * (double)h->ny);
-    const int P = h->pitch;
+    const int P = h->pitch, T = h->tw_state;
     switch (which) {
     case XFB_VORT:
-        return inv2d(h, z, h->spec_b, dout, scale, 0);
+        if (launch_pw(h, OP_COPY, z, P, h->spec_a, P, P, T, 0)) return XFB_E_CUDA;
+        return inv2d(h, h->spec_a, h->spec_b, dout, scale, 0);
     case XFB_PSI:
-        if (launch_pw(h, OP_INVLAP, z, P, h->spec_a, P, P)) return XFB_E_CUDA;
+        if (launch_pw(h, OP_INVLAP, z, P, h->spec_a, P, P, T, 0)) return XFB_E_CUDA;
         return inv2d(h, h->spec_a, h->spec_b, dout, scale, 0);
     case XFB_U:
-        if (launch_pw(h, OP_INVLAP, z, P, h->spec_a, P, P)) return XFB_E_CUDA;
+        if (launch_pw(h, OP_INVLAP, z, P, h->spec_a, P, P, T, 0)) return XFB_E_CUDA;
         if (launch_pw(h, OP_GRADY, h->spec_a, P, h->spec_a, P, P)) return XFB_E_CUDA;
         return inv2d(h, h->spec_a, h->spec_b, dout, scale, 1);
     case XFB_V:
-        if (launch_pw(h, OP_INVLAP, z, P, h->spec_a, P, P)) return XFB_E_CUDA;
+        if (launch_pw(h, OP_INVLAP, z, P, h->spec_a, P, P, T, 0)) return XFB_E_CUDA;
         if (launch_pw(h, OP_GRADX, h->spec_a, P, h->spec_a, P, P)) return XFB_E_CUDA;
         return inv2d(h, h->spec_a, h->spec_b, dout, scale, 0);
     case XFB_DVORTDX:
-        if (launch_pw(h, OP_GRADX, z, P, h->spec_a, P, P)) return XFB_E_CUDA;
+        if (launch_pw(h, OP_GRADX, z, P, h->spec_a, P, P, T, 0)) return XFB_E_CUDA;
         return inv2d(h, h->spec_a, h->spec_b, dout, scale, 0);
     case XFB_DVORTDY:
-        if (launch_pw(h, OP_GRADY, z, P, h->spec_a, P, P)) return XFB_E_CUDA;
+        if (launch_pw(h, OP_GRADY, z, P, h->spec_a, P, P, T, 0)) return XFB_E_CUDA;
         return inv2d(h, h->spec_a, h->spec_b, dout, scale, 0);
     }
     return fail(XFB_E_ARG, "bad field id %d", which);
@@ -583,7 +597,7 @@ static int psi_second(xfb_handle h, int member, int which, float *dout)
     const cpx *z = h->z0 + (size_t)member * h->hpad;
     const float scale = 1.0f / (float)((double)h->nx * (double)h->ny);
     const int P = h->pitch;
-    if (launch_pw(h, OP_INVLAP, z, P, h->spec_a, P, P)) return XFB_E_CUDA;
+    if (launch_pw(h, OP_INVLAP, z, P, h->spec_a, P, P, h->tw_state, 0)) return XFB_E_CUDA;
     if (launch_pw(h, which == 2 ? OP_GRADY : OP_GRADX, h->spec_a, P, h->spec_a, P, P)) return XFB_E_CUDA;
     if (launch_pw(h, which == 1 ? OP_GRADX : OP_GRADY, h->spec_a, P, h->spec_a, P, P)) return XFB_E_CUDA;
     return inv2d(h, h->spec_a, h->spec_b, dout, scale, 0);

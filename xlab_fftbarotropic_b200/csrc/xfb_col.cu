@@ -19,7 +19,7 @@ int col_tile_width(int nx)
     static const int forced = env_int("XFB_COL_W", 0);
     switch (nx) {
     case 256: case 512: case 1024: case 2048: return 4;
-    case 4096: return (forced == 2 || forced == 4) ? forced : 4;
+    case 4096: return (forced == 2 || forced == 4) ? forced : 2;
     case 8192: return (forced == 1 || forced == 2) ? forced : 2;
     case 16384: return 1;
     default: return 0;

@@ -32,6 +32,12 @@ struct ColParams {
     const double *kx2;    // [NX]    (double)kx*kx
     const double *ky2;    // [pitch]
     int pitch;
+    // layout of the K-COL-private state arrays z0/zk/acc: element (i, j0 + c) of column tile b lives at
+    //   member_offset + b * st_tile_stride + i * st_row_stride + c
+    // row-major (operator tier):  st_tile_stride = W,      st_row_stride = pitch
+    // tile-major (stepper):       st_tile_stride = NX * W, st_row_stride = W   (a tile is one contiguous block)
+    long long st_tile_stride;
+    int st_row_stride;
     long long member_stride;   // complex elements between ensemble members
     int ny;               // for the mask reflection nothing is needed in y; kept for clarity
     double mask_kd;       // generalized_wavenumber_square (fftwfop.cpp:57), as stored in float
@@ -103,6 +109,8 @@ col_kernel(const ColParams p)
 
     const int j0 = blockIdx.x * W;
     const size_t moff = (size_t)blockIdx.y * (size_t)p.member_stride;
+    const size_t soff = moff + (size_t)blockIdx.x * (size_t)p.st_tile_stride;   // state arrays: this tile
+    const size_t srow = (size_t)p.st_row_stride;
 
     int t[NIT], c[NIT];
     LineTw<NX> tw[NIT];
@@ -131,7 +139,7 @@ col_kernel(const ColParams p)
             // the epilogue operands of this tile: start them towards L2 now, they are needed after the
             // forward transform (three passes from here)
             for (int r = threadIdx.x; r < NX; r += C::THREADS) {
-                const size_t e = moff + (size_t)r * p.pitch + j0;
+                const size_t e = soff + (size_t)r * srow;
                 prefetch_l2(p.z0 + e);
                 if (p.stage != 1) {
                     prefetch_l2(p.zk + e);
@@ -145,22 +153,22 @@ col_kernel(const ColParams p)
             const int j = j0 + c[it];
             const float kyv = __ldg(p.ky + j);
             const float ky2 = kyv * kyv;
-            const size_t e0 = moff + (size_t)t[it] * p.pitch + j;
+            const size_t e0 = soff + (size_t)t[it] * srow + c[it];
             if (MODE == COL_FWD) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) p.z0[e0 + (size_t)(k * G) * p.pitch] = v[it][k];
+                for (int k = 0; k < 16; ++k) p.z0[e0 + (size_t)(k * G) * srow] = v[it][k];
             } else {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     // operands of eight elements in flight at once
                     cpx z0v[8], zkv[8], av[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) z0v[q] = p.z0[e0 + (size_t)((8 * h + q) * G) * p.pitch];
+                    for (int q = 0; q < 8; ++q) z0v[q] = p.z0[e0 + (size_t)((8 * h + q) * G) * srow];
                     if (p.stage != 1) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            zkv[q] = p.zk[e0 + (size_t)((8 * h + q) * G) * p.pitch];
-                            av[q] = p.acc[e0 + (size_t)((8 * h + q) * G) * p.pitch];
+                            zkv[q] = p.zk[e0 + (size_t)((8 * h + q) * G) * srow];
+                            av[q] = p.acc[e0 + (size_t)((8 * h + q) * G) * srow];
                         }
                     } else {
 #pragma unroll
@@ -170,7 +178,7 @@ col_kernel(const ColParams p)
                     for (int q = 0; q < 8; ++q) {
                         const int k = 8 * h + q;
                         const int i = t[it] + k * G;
-                        const size_t e = e0 + (size_t)(k * G) * p.pitch;
+                        const size_t e = e0 + (size_t)(k * G) * srow;
                         const cpx X = v[it][k];
                         // fused path: kx = (signed index) * TWOPI/Lx and -(kx^2 + ky^2) in float32 (<= 2 ulp
                         // from the reference tables; the operator tier keeps the exact expressions)
@@ -236,9 +244,9 @@ col_kernel(const ColParams p)
             if (!KEEP) {
 #pragma unroll
                 for (int it = 0; it < NIT; ++it) {
-                    const cpx *src = zsrc + moff + (size_t)t[it] * p.pitch + j0 + c[it];
+                    const cpx *src = zsrc + soff + (size_t)t[it] * srow + c[it];
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) v[it][k] = src[(size_t)(k * G) * p.pitch];
+                    for (int k = 0; k < 16; ++k) v[it][k] = src[(size_t)(k * G) * srow];
                 }
             }
 #pragma unroll
