@@ -300,7 +300,9 @@ void orc_invert_pres(orc_t *o, const float *psi_in, float *pres, size_t ref_x, s
     orc_c2r(o, dx2_c, dx2); backward_normalize(o, dx2);                           /* :153 */
     orc_c2r(o, dy2_c, dy2); backward_normalize(o, dy2);                           /* :154 */
     orc_c2r(o, dxdy_c, dxdy); backward_normalize(o, dxdy);                        /* :155 */
-    for (int i = 0; i < grids; ++i) gaus[i] = dx2[i] * dy2[i] - powf(dxdy[i], 2.0f); /* :159 */
+    /* :159  `pow(float, 2.0f)` there is the C library's ::pow(double,double) (no `using namespace std` in
+     * invert_pres.cpp): the square and the subtraction are done in double, the float product is promoted */
+    for (int i = 0; i < grids; ++i) gaus[i] = (float)((double)(dx2[i] * dy2[i]) - pow((double)dxdy[i], 2.0));
     orc_r2c(o, gaus, lap_pres_c);                                                 /* :161 */
     orc_laplacian(o, psi_c, tmp_c);                                               /* :164 */
     for (int i = 0; i < hgrids; ++i) {                                            /* :166-169, double intermediates */

@@ -1,0 +1,110 @@
+"""Host C++ programs: generators byte-identical to the reference (CPU), main.out / invert_pres.out against
+the unmodified reference binaries on the same input (GPU)."""
+import hashlib
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "xlab_fftbarotropic_b200", "bin")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_generators_byte_identical_to_reference():
+    md5 = json.load(open(os.path.join(GOLD, "generators.json")))
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "input"))
+        for name, want in md5.items():
+            subprocess.run([os.path.join(BIN, name + ".out")], cwd=d, check=True, stderr=subprocess.DEVNULL)
+            got = hashlib.md5(open(os.path.join(d, "input", "initial_vorticity.bin"), "rb").read()).hexdigest()
+            assert got == want, name
+
+
+def test_fifo_script_reader_formats():
+    """vort_src recipe files are plain text / byte streams; the reader is exercised end to end on the GPU below"""
+    hdr = open(os.path.join(ROOT, "xlab_fftbarotropic_b200", "csrc", "host", "vorticity_source.hpp")).read()
+    assert "SCRIPT" in hdr and "FIFO" in hdr and "EMPTY" in hdr
+
+
+@pytest.mark.gpu
+def test_main_out_matches_reference_binary():
+    from oracle import oracle as orc
+    n, steps, rec = 256, 5, 2
+    g = np.load(os.path.join(GOLD, "ref_n256.npz"))
+    v0 = g["elliptic_init"]
+    ref = orc.run_reference_main(v0, n, 3.0, steps, rec)
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "input"))
+        os.makedirs(os.path.join(d, "output"))
+        v0.tofile(os.path.join(d, "input", "initial_vorticity.bin"))
+        r = subprocess.run([os.path.join(BIN, "main.out"), "-n", str(n), "-t", str(steps), "-r", str(rec)], cwd=d,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "# Step 0, time = 0.00, record now!" in r.stdout and "Program ends. Congrats!" in r.stdout
+        log = [ln.strip() for ln in open(os.path.join(d, "log"))]
+        want = [f"output/{k}_step_{s}.bin" for s in (0, 2, 4) for k in ("vort_src_input", "vort", "psi", "u", "v")]
+        assert log == want                                   # same files, same order as the reference's log
+        for s in (0, 2, 4):
+            for k in ("vort", "psi", "u", "v"):
+                got = np.fromfile(os.path.join(d, f"output/{k}_step_{s}.bin"), dtype="<f4").reshape(n, n)
+                assert rel_l2(got, ref[(k, s)]) < 1e-5, (k, s)
+
+
+@pytest.mark.gpu
+def test_main_out_fifo_forcing_and_invert_pres():
+    from oracle import oracle as orc
+    import fields
+    n = 256
+    v0 = fields.gaussian(n)
+    src = (fields.kuo2004(n) * np.float32(1e-4)).astype(np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "input"))
+        os.makedirs(os.path.join(d, "output"))
+        v0.tofile(os.path.join(d, "input", "initial_vorticity.bin"))
+        # forcing stream: step 0 no change, step 1 new field, steps 2.. no change   (vort_src_input.cpp:43-61)
+        with open(os.path.join(d, "forcing.bin"), "wb") as fh:
+            fh.write(b"\x00")
+            fh.write(b"\x01")
+            fh.write(src.tobytes())
+            fh.write(b"\x00" * 8)
+        r = subprocess.run([os.path.join(BIN, "main.out"), "-n", str(n), "-t", "4", "-r", "3", "-f", "forcing.bin"],
+                           cwd=d, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        o = orc.Oracle(n)
+        o.set_vorticity(v0)
+        o.step(1, 3.0)
+        o.set_source(src)
+        o.step(2, 3.0)
+        got = np.fromfile(os.path.join(d, "output/vort_step_3.bin"), dtype="<f4").reshape(n, n)
+        assert rel_l2(got, o.get_field(orc.VORT)) < 1e-5
+        assert np.array_equal(np.fromfile(os.path.join(d, "output/vort_src_input_step_3.bin"), dtype="<f4").reshape(n, n), src)
+        # pressure inversion pipeline of test/01-runtest/invert.sh: psi_step_N.bin => pres_step_N.bin
+        r2 = subprocess.run([os.path.join(BIN, "invert_pres.out"), "-n", str(n), "-x", "3", "-y", "5"], cwd=d,
+                            input="output/psi_step_3.bin=>output/pres_step_3.bin\nnot a pair\n", capture_output=True, text=True)
+        assert r2.returncode == 0 and "Error reading input: not a pair" in r2.stdout
+        psi = np.fromfile(os.path.join(d, "output/psi_step_3.bin"), dtype="<f4").reshape(n, n)
+        pres = np.fromfile(os.path.join(d, "output/pres_step_3.bin"), dtype="<f4").reshape(n, n)
+        assert rel_l2(pres, o.invert_pres(psi, 3, 5)) < 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_against_golden_reference_files():
+    """the CUDA path against files written by the unmodified reference binary (committed fixtures)"""
+    import xlab_fftbarotropic_b200 as xfb
+    g = np.load(os.path.join(GOLD, "ref_n256.npz"))
+    b = xfb.Backend(256)
+    b.set_vorticity(g["elliptic_init"])
+    b.step(1, 3.0)
+    for kind, which in (("vort", xfb.capi.VORT), ("psi", xfb.capi.PSI), ("u", xfb.capi.U), ("v", xfb.capi.V)):
+        assert rel_l2(b.get_field(which), g[f"elliptic_{kind}_1"]) < 1e-5, kind
+    assert rel_l2(b.invert_pres(g["elliptic_psi_1"], 3, 5), g["elliptic_pres_1"]) < 1e-5
+    b.set_vorticity(g["kuo_init"])
+    b.step(10, 3.0)
+    assert rel_l2(b.get_field(xfb.capi.VORT), g["kuo_vort_10"]) < 1e-5
+    b.close()

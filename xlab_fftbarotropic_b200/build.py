@@ -61,5 +61,38 @@ def build_library(force: bool = False) -> str:
     return LIB
 
 
+HOST = os.path.join(CSRC, "host")
+BIN = os.path.join(HERE, "bin")
+GENERATORS = {"makefield-elliptic-vortex": 1, "makefield-const-vortex": 2, "makefield-gaussian": 3, "makefield-Kuo2004": 4}
+
+
+def _gxx(out, sources, extra=()):
+    deps = sources + [os.path.join(HOST, f) for f in os.listdir(HOST)] + [os.path.join(ROOT, "include", "xfb.h")]
+    if _mtime(out) >= max(_mtime(d) for d in deps) and _mtime(out) >= _mtime(LIB):
+        return out
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", out, *sources, *extra]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError(f"g++ failed on {out}")
+    return out
+
+
+def build_host() -> dict:
+    """Host C++ programs (I/O and control only; all arithmetic goes through libxfb.so):
+    bin/main.out, bin/invert_pres.out, bin/makefield-*.out"""
+    build_library()
+    os.makedirs(BIN, exist_ok=True)
+    fio = os.path.join(HOST, "fieldio.cpp")
+    link = ["-L", HERE, "-lxfb", "-Wl,-rpath,$ORIGIN/.."]
+    out = {}
+    out["main"] = _gxx(os.path.join(BIN, "main.out"), [os.path.join(HOST, "main.cpp"), fio], link)
+    out["invert_pres"] = _gxx(os.path.join(BIN, "invert_pres.out"), [os.path.join(HOST, "invert_pres.cpp"), fio], link)
+    for name, gen in GENERATORS.items():
+        out[name] = _gxx(os.path.join(BIN, name + ".out"), [os.path.join(HOST, "makefield.cpp"), fio], [f"-DXFB_GEN={gen}"])
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv))
+    print(build_host())

@@ -603,7 +603,7 @@ static int psi_second(xfb_handle h, int member, int which, float *dout)
     return inv2d(h, h->spec_a, h->spec_b, dout, scale, 0);
 }
 
-// filamentation time and deformation factor from psi_xy, psi_xx, psi_yy (oracle: orc_diagnostics)
+// filamentation time and deformation factor from psi_xy, psi_xx, psi_yy
 __global__ void diag_kernel(const float *pxy, const float *pxx, const float *pyy, float *out, long long n, int which)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -649,7 +649,7 @@ extern "C" int xfb_get_field(xfb_handle h, int member, int which, float *out)
     return stage_out(h, out, dout, bytes);
 }
 
-// histogram of area and |grad zeta|^2 over tracer bins (oracle: orc_keff_hist)
+// histogram of area and |grad zeta|^2 over tracer bins
 __global__ void keff_hist_kernel(const float *c, const float *gx, const float *gy, long long n, int nbins, float cmin,
                                  float scale, double da, double *area, double *grad2)
 {
@@ -703,7 +703,8 @@ __global__ void gauss_curv_kernel(const float *dx2, const float *dy2, const floa
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[i] = __fsub_rn(__fmul_rn(dx2[i], dy2[i]), __fmul_rn(dxdy[i], dxdy[i]));     // invert_pres.cpp:159
+    // invert_pres.cpp:159: float product, then `pow(float, 2.0f)` = ::pow(double,double) and a double subtraction
+    out[i] = (float)((double)__fmul_rn(dx2[i], dy2[i]) - (double)dxdy[i] * (double)dxdy[i]);
 }
 
 // lap_pres_c = rho * (f * tmp_c + 2.0 * lap_pres_c), float64 intermediates        (invert_pres.cpp:166-169)

@@ -7,7 +7,7 @@
 //         Jacobian + source loop (:225-227) and the R2C of the tendency (:237), chained in
 //         registers -- the physical-space fields never touch HBM.
 // A real line of NY points is transformed as a complex line of L = NY/2 points plus the
-// standard split/merge step (same algebra as oracle/fftw3_shim/shim_fft.c, different code).
+// standard split/merge step of a half-length real transform.
 #pragma once
 #include "xfb_fft.cuh"
 
