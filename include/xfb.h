@@ -32,7 +32,7 @@ enum {
     XFB_E_SIZE = -2,     /* grid size not supported by the kernels */
     XFB_E_CUDA = -3,     /* CUDA runtime error (message in xfb_last_error) */
     XFB_E_STATE = -4,    /* call order (e.g. step before set_vorticity) */
-    XFB_E_NCCL = -5
+    XFB_E_NCCL = -5      /* NCCL error or libnccl.so.2 not loadable (slab-decomposed handles only) */
 };
 
 /* fields of xfb_get_field */
@@ -103,6 +103,35 @@ int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cma
 
 /* ---- pressure inversion: replaces the loop body of src/invert_pres.cpp:132-187 ---------------*/
 int xfb_invert_pres(xfb_handle h, const float *psi, float *pres, size_t ref_x, size_t ref_y, float rho, float f);
+
+/* ---- slab decomposition of one large grid over the GPUs of a node ------------------------------
+ * No reference equivalent (src/main.cpp is single-threaded); SURVEY.md section 8(e).
+ * Rank r of `nranks` holds the physical rows [row0, row0+rows) and, in spectral space, `cols`
+ * columns starting at col0, cut into `nchunks` chunks of chunk_cols columns (the unit of the
+ * compute/communication overlap); every 2-D transform is a local 1-D pass, an all-to-all over
+ * NVLink and the other local 1-D pass.  xfb_slab_partition is pure host arithmetic. */
+int xfb_slab_partition(int nx, int ny, int nranks, int nchunks, int rank, int *row0, int *rows, int *col0, int *cols,
+                       int *chunk_cols, int *pitch_global);
+/* one process per GPU: rank 0 calls xfb_nccl_unique_id and hands the 128 bytes to the other ranks
+ * (MPI, torch.distributed, a file ...); all ranks then call xfb_create_dist collectively.
+ * On such a handle xfb_set_vorticity / xfb_set_source / xfb_get_field take and return the LOCAL
+ * rows [rows][ny] and are collective, like xfb_step; the operator tier is not available. */
+int xfb_nccl_unique_id(char *id128);
+int xfb_create_dist(xfb_handle *h, int nx, int ny, float lx, float ly, float nu, int device, int rank, int nranks,
+                    int nchunks, const char *id128);
+/* summed milliseconds of the all-to-all exchanges since xfb_profile(h, 1) (NCCL handles) */
+int xfb_profile_read_a2a(xfb_handle h, double *a2a_ms, long long *exchanges);
+/* loopback team: all ranks of a slab decomposition in ONE process on ONE device, exchanging by
+ * device copies.  Same kernels and indexing as the NCCL path; exists so the decomposition can be
+ * verified on a single GPU.  Fields are full [nx][ny] host arrays. */
+typedef struct xfb_loopback_s *xfb_loopback;
+int xfb_loopback_create(xfb_loopback *t, int nx, int ny, float lx, float ly, float nu, int device, int nranks, int nchunks);
+int xfb_loopback_destroy(xfb_loopback t);
+int xfb_loopback_set_vorticity(xfb_loopback t, const float *vort);
+int xfb_loopback_set_source(xfb_loopback t, const float *src);
+int xfb_loopback_step(xfb_loopback t, int nsteps, float dt);
+int xfb_loopback_get_field(xfb_loopback t, int which, float *out);
+long long xfb_loopback_launch_count(xfb_loopback t);
 
 /* ---- introspection --------------------------------------------------------------------------*/
 /* number of CUDA kernels this handle has launched so far */

@@ -1,0 +1,153 @@
+"""Slab decomposition: host arithmetic and the exchange indexing on CPU, the real kernels on GPU.
+
+CPU (`-m "not gpu"`):
+  * xfb_slab_partition covers every row and column exactly once;
+  * a numpy model of the panel / chunk layouts of csrc/xfb_dist.cu (row_off / col_off) run by TWO gloo ranks:
+    local r2c along y -> all-to-all -> c2c along x must equal numpy's rfft2 of the full field, and back.
+GPU (`-m gpu`): the loopback team (all ranks on one device, same kernels and indexing as the NCCL path) must
+reproduce the single-GPU backend to float32 rounding (the same butterflies in the same order; the slab
+instantiation of K-ROW is a different template instance, so the compiler's FMA contraction may differ).
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import fields
+from conftest import rel_l2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("n,p,c", [(256, 2, 1), (512, 4, 2), (1024, 8, 4), (16384, 8, 4), (8192, 2, 4)])
+def test_partition_covers_grid(n, p, c):
+    import xlab_fftbarotropic_b200 as xfb
+    parts = [xfb.slab_partition(n, n, p, c, r) for r in range(p)]
+    assert sum(q["rows"] for q in parts) == n
+    assert [q["row0"] for q in parts] == [r * (n // p) for r in range(p)]
+    assert all(q["rows"] % (2 * c) == 0 for q in parts), "row pairs and row chunks stay on one rank"
+    cw = parts[0]["chunk_cols"]
+    assert cw % 4 == 0 and all(q["chunk_cols"] == cw and q["cols"] == c * cw for q in parts)
+    assert [q["col0"] for q in parts] == [r * c * cw for r in range(p)]
+    assert parts[0]["pitch_global"] == p * c * cw >= n // 2 + 1
+    assert parts[0]["pitch_global"] - (n // 2 + 1) < 4 * p * c + 4, "padding stays small"
+
+
+def test_partition_rejects_bad_arguments():
+    import xlab_fftbarotropic_b200 as xfb
+    with pytest.raises(xfb.XfbError):
+        xfb.slab_partition(256, 256, 3, 1, 0)          # 256 rows do not split into 3 x pairs
+    with pytest.raises(xfb.XfbError):
+        xfb.slab_partition(256, 256, 2, 1, 2)          # rank out of range
+
+
+# ---- numpy model of the exchange, run by two gloo ranks ------------------------------------------------
+def _row_off(q, c, r0, C, rows, cw):
+    return ((q * C + c) * rows + r0) * cw
+
+
+def _col_off(q, c, r0, C, rows, cw, nx):
+    return (c * nx + q * rows + r0) * cw
+
+
+def _slab_worker(rank, world, port, n, C, out):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import xlab_fftbarotropic_b200 as xfb
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    part = xfb.slab_partition(n, n, world, C, rank)
+    rows, cw, pg = part["rows"], part["chunk_cols"], part["pitch_global"]
+    full = fields.elliptic(n).astype(np.float64)
+    mine = full[part["row0"]:part["row0"] + rows]
+    # K-ROW: y transform of the local rows, written into panels (q, c) = [rows][cw] (pair interleave is a
+    # permutation inside a block and does not change which block an element is in)
+    y = np.zeros((rows, pg), np.complex128)
+    y[:, :n // 2 + 1] = np.fft.rfft(mine, axis=1)
+    row_side = np.zeros(world * C * rows * cw, np.complex128)
+    for q in range(world):
+        for c in range(C):
+            o = _row_off(q, c, 0, C, rows, cw)
+            row_side[o:o + rows * cw] = y[:, (q * C + c) * cw:(q * C + c + 1) * cw].ravel()
+    # all-to-all: block (q, c) goes to rank q and lands in chunk c, rows block `rank`
+    col_side = np.zeros(C * n * cw, np.complex128)
+    send = [torch.from_numpy(np.concatenate([row_side[_row_off(q, c, 0, C, rows, cw):_row_off(q, c, 0, C, rows, cw) + rows * cw]
+                                             for c in range(C)]).view(np.float64).copy()) for q in range(world)]
+    # grouped point-to-point like the ncclSend/ncclRecv group of xfb_dist.cu; the own block is a local copy
+    recv = [torch.empty_like(send[0]) for _ in range(world)]
+    recv[rank].copy_(send[rank])
+    ops = []
+    for q in range(world):
+        if q != rank:
+            ops.append(dist.P2POp(dist.isend, send[q], q))
+            ops.append(dist.P2POp(dist.irecv, recv[q], q))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    for q in range(world):
+        blk = recv[q].numpy().view(np.complex128)
+        for c in range(C):
+            o = _col_off(q, c, 0, C, rows, cw, n)
+            col_side[o:o + rows * cw] = blk[c * rows * cw:(c + 1) * rows * cw]
+    # K-COL: x transform of each chunk [n][cw]
+    spec = np.concatenate([np.fft.fft(col_side[c * n * cw:(c + 1) * n * cw].reshape(n, cw), axis=0) for c in range(C)], axis=1)
+    ref = np.zeros((n, pg), np.complex128)
+    ref[:, :n // 2 + 1] = np.fft.rfft2(full)
+    err = np.abs(spec - ref[:, part["col0"]:part["col0"] + C * cw]).max() / np.abs(ref).max()
+    out.put((rank, float(err)))
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("n,C", [(64, 1), (128, 2)])
+def test_exchange_indexing_two_gloo_ranks(n, C):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, n, C, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err in res:
+        assert err < 1e-12, f"rank {rank}: slab 2-D transform differs from rfft2 by {err}"
+
+
+# ---- GPU: loopback team against the single-GPU backend ----------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p,c", [(256, 2, 1), (512, 4, 2), (1024, 2, 4), (512, 8, 1)])
+def test_loopback_team_matches_single_gpu(n, p, c):
+    import xlab_fftbarotropic_b200 as xfb
+    v0 = fields.kuo2004(n) if hasattr(fields, "kuo2004") else fields.elliptic(n)
+    rng = np.random.default_rng(n + p)
+    src = (1e-9 * rng.standard_normal((n, n))).astype(np.float32)
+    one = xfb.Backend(n)
+    team = xfb.LoopbackTeam(n, p, c)
+    one.set_vorticity(v0)
+    team.set_vorticity(v0)
+    one.set_source(src)
+    team.set_source(src)
+    one.step(3, 3.0)
+    team.step(3, 3.0)
+    for which in (xfb.capi.VORT, xfb.capi.PSI, xfb.capi.U, xfb.capi.V, xfb.capi.DEFORM):
+        a, b = one.get_field(which), team.get_field(which)
+        assert rel_l2(b, a) < 2e-6 and np.abs(a - b).max() <= 2e-6 * np.abs(a).max(), f"field {which}: {rel_l2(b, a)}"
+    # stepping again after the record fields were taken (the prologue is redone)
+    one.step(1, 3.0)
+    team.step(1, 3.0)
+    a, b = one.get_field(xfb.capi.VORT), team.get_field(xfb.capi.VORT)
+    assert rel_l2(b, a) < 2e-6
+    assert team.launch_count > 0
+    one.close()
+    team.close()

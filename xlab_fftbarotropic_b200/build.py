@@ -1,6 +1,6 @@
 """In-tree build of the CUDA library (sm_100a only) and of the host C++ programs.
 
-  libxfb.so        csrc/xfb_row.cu + xfb_col.cu + xfb_api.cu  (the C ABI of include/xfb.h)
+  libxfb.so        csrc/xfb_row.cu + xfb_col.cu + xfb_api.cu + xfb_dist.cu  (the C ABI of include/xfb.h)
 
 nvcc cross-compiles without a GPU; the .so is git-ignored but travels with gpurun snapshots.
 """
@@ -20,8 +20,8 @@ LIB = os.path.join(HERE, "libxfb.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
-CUDA_SOURCES = ["xfb_row.cu", "xfb_col.cu", "xfb_api.cu"]
-HEADERS = ["xfb_fft.cuh", "xfb_row.cuh", "xfb_col.cuh", "xfb_internal.h", os.path.join(ROOT, "include", "xfb.h")]
+CUDA_SOURCES = ["xfb_row.cu", "xfb_col.cu", "xfb_api.cu", "xfb_dist.cu"]
+HEADERS = ["xfb_fft.cuh", "xfb_row.cuh", "xfb_col.cuh", "xfb_internal.h", "xfb_handle.h", os.path.join(ROOT, "include", "xfb.h")]
 
 
 def _mtime(p):
@@ -53,7 +53,7 @@ def build_library(force: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(CUDA_SOURCES)) as ex:
         objs = list(ex.map(_compile, CUDA_SOURCES))
     if _mtime(LIB) < max(_mtime(o) for o in objs):
-        r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+        r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"],
                            capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

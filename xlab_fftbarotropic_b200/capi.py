@@ -21,6 +21,9 @@ SYMBOLS = [
     "xfb_invert_laplacian", "xfb_dealias", "xfb_get_table", "xfb_r2c", "xfb_c2r", "xfb_set_vorticity",
     "xfb_set_spectrum", "xfb_get_spectrum", "xfb_set_source", "xfb_step", "xfb_get_field", "xfb_get_keff_hist",
     "xfb_invert_pres", "xfb_launch_count", "xfb_stream", "xfb_size_supported", "xfb_profile", "xfb_profile_read",
+    "xfb_slab_partition", "xfb_nccl_unique_id", "xfb_create_dist", "xfb_profile_read_a2a",
+    "xfb_loopback_create", "xfb_loopback_destroy", "xfb_loopback_set_vorticity", "xfb_loopback_set_source",
+    "xfb_loopback_step", "xfb_loopback_get_field", "xfb_loopback_launch_count",
 ]
 
 _lib = None
@@ -62,8 +65,40 @@ def load():
     L.xfb_profile.argtypes = [vp, ci]
     L.xfb_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                                    C.POINTER(C.c_longlong)]
+    ip = C.POINTER(ci)
+    L.xfb_slab_partition.argtypes = [ci, ci, ci, ci, ci, ip, ip, ip, ip, ip, ip]
+    L.xfb_nccl_unique_id.argtypes = [C.c_char_p]
+    L.xfb_create_dist.argtypes = [C.POINTER(vp), ci, ci, cf, cf, cf, ci, ci, ci, ci, C.c_char_p]
+    L.xfb_profile_read_a2a.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    L.xfb_loopback_create.argtypes = [C.POINTER(vp), ci, ci, cf, cf, cf, ci, ci, ci]
+    L.xfb_loopback_destroy.argtypes = [vp]
+    L.xfb_loopback_set_vorticity.argtypes = [vp, vp]
+    L.xfb_loopback_set_source.argtypes = [vp, vp]
+    L.xfb_loopback_step.argtypes = [vp, ci, cf]
+    L.xfb_loopback_get_field.argtypes = [vp, ci, vp]
+    L.xfb_loopback_launch_count.restype = C.c_longlong
+    L.xfb_loopback_launch_count.argtypes = [vp]
     _lib = L
     return L
+
+
+def slab_partition(nx, ny, nranks, nchunks, rank):
+    """-> dict(row0, rows, col0, cols, chunk_cols, pitch_global); pure host arithmetic (no GPU needed)"""
+    L = load()
+    v = [C.c_int() for _ in range(6)]
+    rc = L.xfb_slab_partition(nx, ny, nranks, nchunks, rank, *[C.byref(x) for x in v])
+    if rc != 0:
+        raise XfbError(f"xfb error {rc}: {L.xfb_last_error().decode()}")
+    return dict(zip(("row0", "rows", "col0", "cols", "chunk_cols", "pitch_global"), (x.value for x in v)))
+
+
+def nccl_unique_id() -> bytes:
+    L = load()
+    buf = C.create_string_buffer(128)
+    rc = L.xfb_nccl_unique_id(buf)
+    if rc != 0:
+        raise XfbError(f"xfb error {rc}: {L.xfb_last_error().decode()}")
+    return buf.raw
 
 
 def _ptr(a):
@@ -199,3 +234,83 @@ class Backend:
     @property
     def stream(self):
         return self._L.xfb_stream(self._h)
+
+
+class SlabBackend(Backend):
+    """One rank of a slab-decomposed grid (one process per GPU, NCCL all-to-all).  Fields are the LOCAL rows."""
+
+    def __init__(self, n: int, rank: int, nranks: int, unique_id: bytes, nchunks: int = 4, lx: float = 600000.0,
+                 nu: float = 6.5, device: int = 0):
+        self.nx, self.ny, self.hy, self.batch = n, n, n // 2 + 1, 1
+        self.lx, self.ly, self.nu = lx, lx, nu
+        self.rank, self.nranks = rank, nranks
+        self.part = slab_partition(n, n, nranks, nchunks, rank) if nranks > 1 else dict(row0=0, rows=n)
+        self.rows = self.part["rows"]
+        self._L = load()
+        self._h = C.c_void_p()
+        self._ck(self._L.xfb_create_dist(C.byref(self._h), n, n, lx, lx, nu, device, rank, nranks, nchunks, unique_id))
+
+    def set_vorticity(self, f, member=0):
+        if not isinstance(f, (int, np.integer)):
+            f = np.ascontiguousarray(f, dtype=np.float32).reshape(self.rows, self.ny)
+        self._ck(self._L.xfb_set_vorticity(self._h, 0, _ptr(f)))
+
+    def get_field(self, which, member=0, out=None):
+        if out is None:
+            out = np.empty((self.rows, self.ny), np.float32)
+        self._ck(self._L.xfb_get_field(self._h, 0, which, _ptr(out)))
+        return out
+
+    def a2a_read(self):
+        ms, n = C.c_double(), C.c_longlong()
+        self._ck(self._L.xfb_profile_read_a2a(self._h, C.byref(ms), C.byref(n)))
+        return {"a2a_ms": ms.value, "exchanges": n.value}
+
+
+class LoopbackTeam:
+    """All ranks of a slab decomposition in one process on one device (verification of the slab indexing
+    on a single GPU; same kernels as the NCCL path, the exchange is a set of device copies)."""
+
+    def __init__(self, n: int, nranks: int, nchunks: int = 1, lx: float = 600000.0, nu: float = 6.5, device: int = 0):
+        self.n = n
+        self._L = load()
+        self._t = C.c_void_p()
+        self._ck(self._L.xfb_loopback_create(C.byref(self._t), n, n, lx, lx, nu, device, nranks, nchunks))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise XfbError(f"xfb error {rc}: {self._L.xfb_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_t", None) and self._t.value:
+            self._L.xfb_loopback_destroy(self._t)
+            self._t = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_vorticity(self, f):
+        f = np.ascontiguousarray(f, dtype=np.float32).reshape(self.n, self.n)
+        self._ck(self._L.xfb_loopback_set_vorticity(self._t, _ptr(f)))
+
+    def set_source(self, s):
+        if s is None:
+            self._ck(self._L.xfb_loopback_set_source(self._t, None))
+        else:
+            s = np.ascontiguousarray(s, dtype=np.float32).reshape(self.n, self.n)
+            self._ck(self._L.xfb_loopback_set_source(self._t, _ptr(s)))
+
+    def step(self, nsteps, dt):
+        self._ck(self._L.xfb_loopback_step(self._t, int(nsteps), float(dt)))
+
+    def get_field(self, which):
+        out = np.empty((self.n, self.n), np.float32)
+        self._ck(self._L.xfb_loopback_get_field(self._t, which, _ptr(out)))
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self._L.xfb_loopback_launch_count(self._t))

@@ -7,8 +7,7 @@
 #include <new>
 #include <vector>
 
-#include "../../include/xfb.h"
-#include "xfb_internal.h"
+#include "xfb_handle.h"
 
 using namespace xfb;
 
@@ -17,7 +16,7 @@ using namespace xfb;
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char *fmt, ...)
+int xfb::fail(int code, const char *fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -28,52 +27,7 @@ static int fail(int code, const char *fmt, ...)
 
 extern "C" const char *xfb_last_error(void) { return g_err; }
 
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e__ = (call);                                                                  \
-        if (e__ != cudaSuccess) return fail(XFB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
-    } while (0)
-
-#define CKL(h, call)                                                                                       \
-    do {                                                                                                   \
-        int e__ = (call);                                                                                  \
-        if (e__ != 0) return fail(XFB_E_CUDA, "%s: %s", #call, cudaGetErrorString((cudaError_t)e__));      \
-        (h)->launches++;                                                                                   \
-    } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// handle
-// ------------------------------------------------------------------------------------------------
-struct xfb_handle_s {
-    int nx, ny, hy, pitch, batch, device;
-    int tw_state;        // column tile width = tile-major layout of z0/zk/acc
-    float lx, ly, nu;
-    size_t grids, hgrids, hpad;   // per member: nx*ny, nx*(ny/2+1), nx*pitch
-    cudaStream_t stream;
-    // tables
-    cpx *tw;
-    int twn;
-    float *kx, *ky;
-    double *kx2, *ky2;
-    double mask_kd;
-    // stepper state (padded layout [batch][nx][pitch])
-    cpx *z0, *zk, *acc, *jint, *t[4];
-    float *src;          // [batch][nx][ny], allocated on first use
-    bool has_src;
-    bool have_state;     // a vorticity/spectrum has been set
-    bool tf_valid;       // t[0..3] hold the prologue of the current z0
-    // scratch for the operator tier / record path (one member)
-    float *real_a, *real_b, *real_c;
-    cpx *spec_a, *spec_b;      // padded layout
-    float *ref_a, *ref_b;      // reference layout half spectra (2*hgrids floats)
-    long long launches;
-    // optional per-kernel timing (xfb_profile)
-    bool profiling;
-    std::vector<cudaEvent_t> *ev_row, *ev_col;   // pairs (begin, end)
-    size_t ev_row_used, ev_col_used;
-};
-
-static cudaEvent_t next_event(std::vector<cudaEvent_t> *pool, size_t &used)
+cudaEvent_t xfb::next_event(std::vector<cudaEvent_t> *pool, size_t &used)
 {
     if (used == pool->size()) {
         cudaEvent_t e;
@@ -83,14 +37,14 @@ static cudaEvent_t next_event(std::vector<cudaEvent_t> *pool, size_t &used)
     return (*pool)[used++];
 }
 
-static int dev_alloc(void **p, size_t bytes)
+int xfb::dev_alloc(void **p, size_t bytes)
 {
     cudaError_t e = cudaMalloc(p, bytes);
     if (e != cudaSuccess) return fail(XFB_E_CUDA, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
     return 0;
 }
 
-static bool is_device_ptr(const void *p)
+bool xfb::is_device_ptr(const void *p)
 {
     cudaPointerAttributes a;
     cudaError_t e = cudaPointerGetAttributes(&a, p);
@@ -107,13 +61,13 @@ extern "C" int xfb_size_supported(int nx, int ny)
 // ------------------------------------------------------------------------------------------------
 // pointwise kernels (operator tier, layout conversion, physical-space helpers)
 // ------------------------------------------------------------------------------------------------
-enum { OP_GRADX = 0, OP_GRADY = 1, OP_LAP = 2, OP_INVLAP = 3, OP_DEALIAS = 4, OP_COPY = 5 };
 
 struct PwParams {
     const cpx *in;
     cpx *out;
     int nx, in_pitch, out_pitch, ncols;   // ncols columns are processed; the rest of out's pitch is zeroed
     int in_tw, out_tw;                    // > 0: that side is in the stepper's tile-major layout, tile width tw
+    int j_base;                           // global index of column 0 (slab runs)
     const float *kx, *ky;
     const double *kx2, *ky2;
     double mask_kd;
@@ -127,6 +81,7 @@ __global__ void pointwise_kernel(const PwParams p)
     const long long total = (long long)p.nx * p.out_pitch;
     if (idx >= total) return;
     const int i = (int)(idx / p.out_pitch), j = (int)(idx % p.out_pitch);
+    const int jg = p.j_base + j;
     const size_t oidx = p.out_tw ? ((size_t)(j / p.out_tw) * p.nx + i) * p.out_tw + (j % p.out_tw) : (size_t)idx;
     if (j >= p.ncols) { p.out[oidx] = mk(0.f, 0.f); return; }
     const cpx z = p.in_tw ? p.in[((size_t)(j / p.in_tw) * p.nx + i) * p.in_tw + (j % p.in_tw)]
@@ -134,16 +89,16 @@ __global__ void pointwise_kernel(const PwParams p)
     cpx r = z;
     switch (p.op) {
     case OP_GRADX: { const float k = p.kx[i]; r = mk(__fmul_rn(-z.y, k), __fmul_rn(z.x, k)); break; }
-    case OP_GRADY: { const float k = p.ky[j]; r = mk(__fmul_rn(-z.y, k), __fmul_rn(z.x, k)); break; }
-    case OP_LAP: { const float l = lap_coe(p.kx2[i], p.ky2[j]); r = mk(__fmul_rn(z.x, l), __fmul_rn(z.y, l)); break; }
+    case OP_GRADY: { const float k = p.ky[jg]; r = mk(__fmul_rn(-z.y, k), __fmul_rn(z.x, k)); break; }
+    case OP_LAP: { const float l = lap_coe(p.kx2[i], p.ky2[jg]); r = mk(__fmul_rn(z.x, l), __fmul_rn(z.y, l)); break; }
     case OP_INVLAP: {
-        const float l = (i == 0 && j == 0) ? 1.0f : lap_coe(p.kx2[i], p.ky2[j]);
+        const float l = (i == 0 && jg == 0) ? 1.0f : lap_coe(p.kx2[i], p.ky2[jg]);
         r = mk(__fdiv_rn(z.x, l), __fdiv_rn(z.y, l));
         break;
     }
     case OP_DEALIAS: {
         const long long ii = (i <= p.nx / 2) ? i : p.nx - i;
-        const float m = ((double)(ii * ii + (long long)j * j) >= p.mask_kd) ? 0.0f : 1.0f;
+        const float m = ((double)(ii * ii + (long long)jg * jg) >= p.mask_kd) ? 0.0f : 1.0f;
         r = mk(__fmul_rn(z.x, m), __fmul_rn(z.y, m));
         break;
     }
@@ -167,12 +122,12 @@ __global__ void table_kernel(float *out, int which, int nx, int hy, const double
     }
 }
 
-static int launch_pw(xfb_handle h, int op, const cpx *in, int in_pitch, cpx *out, int out_pitch, int ncols,
-                     int in_tw = 0, int out_tw = 0)
+int xfb::launch_pw(xfb_handle h, int op, const cpx *in, int in_pitch, cpx *out, int out_pitch, int ncols, int in_tw, int out_tw,
+                   int chunk)
 {
     PwParams p;
     p.in = in; p.out = out; p.nx = h->nx; p.in_pitch = in_pitch; p.out_pitch = out_pitch; p.ncols = ncols;
-    p.in_tw = in_tw; p.out_tw = out_tw;
+    p.in_tw = in_tw; p.out_tw = out_tw; p.j_base = h->col0 + chunk * h->pitch;
     p.kx = h->kx; p.ky = h->ky; p.kx2 = h->kx2; p.ky2 = h->ky2; p.mask_kd = h->mask_kd; p.op = op;
     const long long total = (long long)h->nx * out_pitch;
     const int threads = 256;
@@ -186,11 +141,33 @@ static int launch_pw(xfb_handle h, int op, const cpx *in, int in_pitch, cpx *out
 // ------------------------------------------------------------------------------------------------
 // create / destroy
 // ------------------------------------------------------------------------------------------------
-extern "C" int xfb_create(xfb_handle *out, int nx, int ny, float lx, float ly, float nu, int batch, int device)
+extern "C" int xfb_slab_partition(int nx, int ny, int nranks, int nchunks, int rank, int *row0, int *rows, int *col0,
+                                  int *cols, int *chunk_cols, int *pitch_global)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(XFB_E_ARG, "xfb_slab_partition: bad rank %d of %d", rank, nranks);
+    if (nchunks < 1 || nchunks > 16) return fail(XFB_E_ARG, "xfb_slab_partition: nchunks %d not in 1..16", nchunks);
+    if (nx % (2 * nranks) != 0)
+        return fail(XFB_E_SIZE, "xfb_slab_partition: nx=%d is not a multiple of 2 x %d ranks (row pairs stay on one rank)", nx, nranks);
+    const int hy = ny / 2 + 1, panels = nranks * nchunks;
+    int cw = (hy + panels - 1) / panels;
+    cw = (cw + 3) / 4 * 4;                                  // whole column tiles, 32-byte aligned panels
+    if (panels == 1) cw = ny / 2 + 4;
+    if (row0) *row0 = rank * (nx / nranks);
+    if (rows) *rows = nx / nranks;
+    if (col0) *col0 = rank * nchunks * cw;
+    if (cols) *cols = nchunks * cw;
+    if (chunk_cols) *chunk_cols = cw;
+    if (pitch_global) *pitch_global = cw * panels;
+    return 0;
+}
+
+int xfb::create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float nu, int batch, int device, int rank, int nranks,
+                     int nchunks)
 {
     if (!out) return fail(XFB_E_ARG, "xfb_create: null handle pointer");
     *out = nullptr;
     if (batch < 1) return fail(XFB_E_ARG, "xfb_create: batch must be >= 1");
+    if (nranks > 1 && batch != 1) return fail(XFB_E_ARG, "slab handles hold one member");
     if (!xfb_size_supported(nx, ny))
         return fail(XFB_E_SIZE, "xfb_create: grid %dx%d not supported (powers of two 256..16384)", nx, ny);
     int ndev = 0;
@@ -204,10 +181,22 @@ extern "C" int xfb_create(xfb_handle *out, int nx, int ny, float lx, float ly, f
     xfb_handle h = new (std::nothrow) xfb_handle_s();
     if (!h) return fail(XFB_E_ARG, "xfb_create: out of host memory");
     memset(h, 0, sizeof(*h));
-    h->nx = nx; h->ny = ny; h->hy = ny / 2 + 1; h->pitch = ny / 2 + 4; h->batch = batch; h->device = device;
+    h->nx = nx; h->ny = ny; h->hy = ny / 2 + 1; h->batch = batch; h->device = device;
     h->lx = lx; h->ly = ly; h->nu = nu;
     h->tw_state = col_tile_width(nx);
-    h->grids = (size_t)nx * ny; h->hgrids = (size_t)nx * h->hy; h->hpad = (size_t)nx * h->pitch;
+    h->rank = rank; h->nranks = nranks; h->nchunks = nchunks;
+    {
+        int row0, cols;
+        if (xfb_slab_partition(nx, ny, nranks, nchunks, rank, &row0, &h->rows, &h->col0, &cols, &h->pitch, &h->pitch_g))
+            return XFB_E_SIZE;
+        // k / cw by multiply-high: verified for every column index the kernels can form
+        h->cw_magic = (unsigned)(((1ull << 32) + h->pitch - 1) / h->pitch);
+        for (unsigned k = 0; k < (unsigned)h->pitch_g; ++k)
+            if ((unsigned)(((unsigned long long)k * h->cw_magic) >> 32) != k / (unsigned)h->pitch)
+                return fail(XFB_E_SIZE, "internal: magic division fails for k=%u cw=%d", k, h->pitch);
+    }
+    // `pitch` is the pitch of the column-side arrays (one chunk of this rank's columns; all columns on one GPU)
+    h->grids = (size_t)h->rows * ny; h->hgrids = (size_t)nx * h->hy; h->hpad = (size_t)nx * h->pitch * nchunks;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 
     // master twiddle table exp(-2 pi i k / twn), float64 -> float32 once
@@ -224,20 +213,21 @@ extern "C" int xfb_create(xfb_handle *out, int nx, int ny, float lx, float ly, f
     // wavenumber tables with the reference's float expressions (fftwfop.cpp:15-24, fftwfop.hpp:7)
     {
         const float TWOPI = acosf(-1.0f) * 2.0f;
-        std::vector<float> kx(nx), ky(h->pitch);
-        std::vector<double> kx2(nx), ky2(h->pitch);
+        const int nky = h->pitch_g;
+        std::vector<float> kx(nx), ky(nky);
+        std::vector<double> kx2(nx), ky2(nky);
         for (int i = 0; i <= nx / 2; ++i) kx[i] = TWOPI * ((float)i) / lx;
         for (int i = nx / 2 + 1; i < nx; ++i) kx[i] = -kx[nx - i];
-        for (int j = 0; j < h->pitch; ++j) ky[j] = TWOPI * ((float)j) / ly;
+        for (int j = 0; j < nky; ++j) ky[j] = TWOPI * ((float)j) / ly;
         for (int i = 0; i < nx; ++i) kx2[i] = (double)kx[i] * (double)kx[i];
-        for (int j = 0; j < h->pitch; ++j) ky2[j] = (double)ky[j] * (double)ky[j];
-        if (dev_alloc((void **)&h->kx, sizeof(float) * nx) || dev_alloc((void **)&h->ky, sizeof(float) * h->pitch) ||
-            dev_alloc((void **)&h->kx2, sizeof(double) * nx) || dev_alloc((void **)&h->ky2, sizeof(double) * h->pitch))
+        for (int j = 0; j < nky; ++j) ky2[j] = (double)ky[j] * (double)ky[j];
+        if (dev_alloc((void **)&h->kx, sizeof(float) * nx) || dev_alloc((void **)&h->ky, sizeof(float) * nky) ||
+            dev_alloc((void **)&h->kx2, sizeof(double) * nx) || dev_alloc((void **)&h->ky2, sizeof(double) * nky))
             return XFB_E_CUDA;
         CK(cudaMemcpy(h->kx, kx.data(), sizeof(float) * nx, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->ky, ky.data(), sizeof(float) * h->pitch, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->ky, ky.data(), sizeof(float) * nky, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(h->kx2, kx2.data(), sizeof(double) * nx, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->ky2, ky2.data(), sizeof(double) * h->pitch, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->ky2, ky2.data(), sizeof(double) * nky, cudaMemcpyHostToDevice));
         // fftwfop.cpp:11-12,57: ceil(((float)N)/3.0) squared and summed in double, stored as float
         const int dkx = (int)ceil(((float)nx) / 3.0), dky = (int)ceil(((float)ny) / 3.0);
         h->mask_kd = (double)(float)((double)dkx * dkx + (double)dky * dky);
@@ -250,33 +240,65 @@ extern "C" int xfb_create(xfb_handle *out, int nx, int ny, float lx, float ly, f
     }
     if (dev_alloc((void **)&h->real_a, sizeof(float) * h->grids) || dev_alloc((void **)&h->real_b, sizeof(float) * h->grids) ||
         dev_alloc((void **)&h->real_c, sizeof(float) * h->grids) ||
-        dev_alloc((void **)&h->spec_a, sizeof(cpx) * h->hpad) || dev_alloc((void **)&h->spec_b, sizeof(cpx) * h->hpad) ||
-        dev_alloc((void **)&h->ref_a, sizeof(cpx) * h->hgrids) || dev_alloc((void **)&h->ref_b, sizeof(cpx) * h->hgrids))
+        dev_alloc((void **)&h->spec_a, sizeof(cpx) * h->hpad) || dev_alloc((void **)&h->spec_b, sizeof(cpx) * h->hpad))
         return XFB_E_CUDA;
+    if (nranks == 1) {
+        if (dev_alloc((void **)&h->ref_a, sizeof(cpx) * h->hgrids) || dev_alloc((void **)&h->ref_b, sizeof(cpx) * h->hgrids))
+            return XFB_E_CUDA;
+    }
     CK(cudaMemsetAsync(h->spec_a, 0, sizeof(cpx) * h->hpad, h->stream));
     CK(cudaMemsetAsync(h->spec_b, 0, sizeof(cpx) * h->hpad, h->stream));
+    if (nranks > 1) {
+        cpx **rb[] = {&h->jint_recv, &h->tr[0], &h->tr[1], &h->tr[2], &h->tr[3]};
+        for (auto pp : rb) {
+            if (dev_alloc((void **)pp, sb)) return XFB_E_CUDA;
+            CK(cudaMemsetAsync(*pp, 0, sb, h->stream));
+        }
+        CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        for (auto &ev : h->ev_chunk) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto &ev : h->ev_comm) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
     CK(cudaStreamSynchronize(h->stream));
     *out = h;
+    return 0;
+}
+
+extern "C" int xfb_create(xfb_handle *out, int nx, int ny, float lx, float ly, float nu, int batch, int device)
+{
+    return create_impl(out, nx, ny, lx, ly, nu, batch, device, 0, 1, 1);
+}
+
+int xfb::destroy_impl(xfb_handle h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+    void *ptrs[] = {h->tw, h->kx, h->ky, h->kx2, h->ky2, h->z0, h->zk, h->acc, h->jint, h->t[0], h->t[1], h->t[2],
+                    h->t[3], h->src, h->real_a, h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b,
+                    h->jint_recv, h->tr[0], h->tr[1], h->tr[2], h->tr[3]};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    for (auto pool : {h->ev_row, h->ev_col, h->ev_a2a})
+        if (pool) {
+            for (cudaEvent_t e : *pool) cudaEventDestroy(e);
+            delete pool;
+        }
+    if (h->comm_stream) {
+        for (auto ev : h->ev_chunk) cudaEventDestroy(ev);
+        for (auto ev : h->ev_comm) cudaEventDestroy(ev);
+        cudaStreamDestroy(h->comm_stream);
+    }
+    cudaStreamDestroy(h->stream);
+    delete h;
     return 0;
 }
 
 extern "C" int xfb_destroy(xfb_handle h)
 {
     if (!h) return 0;
-    cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
-    void *ptrs[] = {h->tw, h->kx, h->ky, h->kx2, h->ky2, h->z0, h->zk, h->acc, h->jint, h->t[0], h->t[1], h->t[2],
-                    h->t[3], h->src, h->real_a, h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b};
-    for (void *p : ptrs)
-        if (p) cudaFree(p);
-    for (auto pool : {h->ev_row, h->ev_col})
-        if (pool) {
-            for (cudaEvent_t e : *pool) cudaEventDestroy(e);
-            delete pool;
-        }
-    cudaStreamDestroy(h->stream);
-    delete h;
-    return 0;
+    if (h->team) { dist_release(h); return 0; }
+    return destroy_impl(h);
 }
 
 extern "C" int xfb_sync(xfb_handle h)
@@ -349,9 +371,15 @@ static int stage_out(xfb_handle h, void *user, const void *dev, size_t bytes)
 // ------------------------------------------------------------------------------------------------
 // operator tier
 // ------------------------------------------------------------------------------------------------
+#define NO_SLAB(h, what)                                                                                        \
+    do {                                                                                                         \
+        if ((h)->nranks > 1) return fail(XFB_E_STATE, what ": not available on a slab-decomposed handle");       \
+    } while (0)
+
 static int spectral_op(xfb_handle h, int op, const float *in, float *out)
 {
     if (!h || !in || !out) return fail(XFB_E_ARG, "null argument");
+    NO_SLAB(h, "spectral operator");
     CK(cudaSetDevice(h->device));
     const size_t bytes = sizeof(cpx) * h->hgrids;
     const void *din;
@@ -370,6 +398,7 @@ extern "C" int xfb_dealias(xfb_handle h, const float *in, float *out) { return s
 extern "C" int xfb_get_table(xfb_handle h, int which, float *out)
 {
     if (!h || !out) return fail(XFB_E_ARG, "null argument");
+    NO_SLAB(h, "xfb_get_table");
     CK(cudaSetDevice(h->device));
     if (which == XFB_TAB_GRADX) { CK(cudaMemcpy(out, h->kx, sizeof(float) * h->nx, cudaMemcpyDeviceToHost)); return 0; }
     if (which == XFB_TAB_GRADY) { CK(cudaMemcpy(out, h->ky, sizeof(float) * h->hy, cudaMemcpyDeviceToHost)); return 0; }
@@ -385,18 +414,22 @@ extern "C" int xfb_get_table(xfb_handle h, int which, float *out)
 }
 
 // ---- 2-D transforms on device buffers ---------------------------------------------------------
-static void fill_row(xfb_handle h, RowParams &p, int nrows)
+void xfb::fill_row(xfb_handle h, RowParams &p, int nrows)
 {
     memset(&p, 0, sizeof(p));
-    p.tw = h->tw; p.twn = h->twn; p.nrows = nrows; p.pitch = h->pitch;
+    p.tw = h->tw; p.twn = h->twn; p.nrows = nrows; p.pitch = h->pitch_g;
     p.scale = 1.0f / (float)((double)h->nx * (double)h->ny);
+    if (h->nranks > 1) {
+        p.cw = h->pitch; p.panel_stride = (long long)h->rows * h->pitch; p.cw_magic = h->cw_magic;
+    }
 }
 
-static void fill_col(xfb_handle h, ColParams &p)
+void xfb::fill_col(xfb_handle h, ColParams &p, int chunk)
 {
     memset(&p, 0, sizeof(p));
     p.tw = h->tw; p.twn = h->twn; p.kx = h->kx; p.ky = h->ky; p.kx2 = h->kx2; p.ky2 = h->ky2;
     p.pitch = h->pitch; p.member_stride = (long long)h->hpad; p.ny = h->ny; p.mask_kd = h->mask_kd; p.nu = h->nu;
+    p.j_base = h->col0 + chunk * h->pitch;
     p.mask_kd_i = (int)h->mask_kd;
     p.st_tile_stride = col_tile_width(h->nx); p.st_row_stride = h->pitch;      // row-major unless the stepper says otherwise
     p.kxscale = (acosf(-1.0f) * 2.0f) / h->lx;
@@ -429,6 +462,7 @@ static int inv2d(xfb_handle h, const cpx *spec_in, cpx *tmp, float *real_out, fl
 extern "C" int xfb_r2c(xfb_handle h, const float *real_in, float *spec_out)
 {
     if (!h || !real_in || !spec_out) return fail(XFB_E_ARG, "null argument");
+    NO_SLAB(h, "xfb_r2c");
     CK(cudaSetDevice(h->device));
     const void *din;
     if (stage_in(h, real_in, h->real_a, sizeof(float) * h->grids, &din)) return XFB_E_CUDA;
@@ -441,6 +475,7 @@ extern "C" int xfb_r2c(xfb_handle h, const float *real_in, float *spec_out)
 extern "C" int xfb_c2r(xfb_handle h, const float *spec_in, float *real_out)
 {
     if (!h || !spec_in || !real_out) return fail(XFB_E_ARG, "null argument");
+    NO_SLAB(h, "xfb_c2r");
     CK(cudaSetDevice(h->device));
     const void *din;
     if (stage_in(h, spec_in, h->ref_a, sizeof(cpx) * h->hgrids, &din)) return XFB_E_CUDA;
@@ -465,6 +500,7 @@ extern "C" int xfb_set_vorticity(xfb_handle h, int member, const float *vort)
     if (check_member(h, member)) return XFB_E_ARG;
     if (!vort) return fail(XFB_E_ARG, "null vorticity");
     CK(cudaSetDevice(h->device));
+    if (h->nranks > 1) return dist_set_vorticity(h, vort);
     const void *din;
     if (stage_in(h, vort, h->real_a, sizeof(float) * h->grids, &din)) return XFB_E_CUDA;
     if (fwd2d(h, (const float *)din, h->spec_a, h->spec_b)) return XFB_E_CUDA;
@@ -480,6 +516,7 @@ extern "C" int xfb_set_spectrum(xfb_handle h, int member, const float *spec)
 {
     if (check_member(h, member)) return XFB_E_ARG;
     if (!spec) return fail(XFB_E_ARG, "null spectrum");
+    NO_SLAB(h, "xfb_set_spectrum");
     CK(cudaSetDevice(h->device));
     const void *din;
     if (stage_in(h, spec, h->ref_a, sizeof(cpx) * h->hgrids, &din)) return XFB_E_CUDA;
@@ -496,6 +533,7 @@ extern "C" int xfb_get_spectrum(xfb_handle h, int member, float *spec)
     if (check_member(h, member)) return XFB_E_ARG;
     if (!spec) return fail(XFB_E_ARG, "null spectrum");
     if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_spectrum before xfb_set_vorticity");
+    NO_SLAB(h, "xfb_get_spectrum");
     CK(cudaSetDevice(h->device));
     void *dout = stage_out_target(spec, h->ref_a);
     if (launch_pw(h, OP_COPY, h->z0 + (size_t)member * h->hpad, h->pitch, (cpx *)dout, h->hy, h->hy, h->tw_state, 0))
@@ -530,6 +568,7 @@ extern "C" int xfb_step(xfb_handle h, int nsteps, float dt)
     if (nsteps < 0) return fail(XFB_E_ARG, "negative step count");
     if (!h->have_state) return fail(XFB_E_STATE, "xfb_step before xfb_set_vorticity");
     CK(cudaSetDevice(h->device));
+    if (h->nranks > 1) return dist_step(h, nsteps, dt);
     ColParams c; fill_col(h, c);
     c.jint = h->jint; c.z0 = h->z0; c.zk = h->zk; c.acc = h->acc;
     c.st_tile_stride = (long long)h->nx * h->tw_state; c.st_row_stride = h->tw_state;     // tile-major state
@@ -621,6 +660,7 @@ extern "C" int xfb_get_field(xfb_handle h, int member, int which, float *out)
     if (!out) return fail(XFB_E_ARG, "null output");
     if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_field before xfb_set_vorticity");
     CK(cudaSetDevice(h->device));
+    if (h->nranks > 1 && which != XFB_SRC) return dist_get_field(h, which, out);
     const size_t bytes = sizeof(float) * h->grids;
     if (which == XFB_SRC) {
         if (!h->src) {
@@ -676,6 +716,7 @@ extern "C" int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin
     if (check_member(h, member)) return XFB_E_ARG;
     if (!area || !grad2 || nbins < 1 || nbins > 2048 || !(cmax > cmin)) return fail(XFB_E_ARG, "bad histogram arguments");
     if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_keff_hist before xfb_set_vorticity");
+    NO_SLAB(h, "xfb_get_keff_hist");
     CK(cudaSetDevice(h->device));
     if (derived_field(h, member, XFB_VORT, h->real_a)) return XFB_E_CUDA;
     if (derived_field(h, member, XFB_DVORTDX, h->real_b)) return XFB_E_CUDA;
@@ -734,6 +775,7 @@ __global__ void zero_one_kernel(float *p, size_t ref) { p[ref] = __fsub_rn(p[ref
 extern "C" int xfb_invert_pres(xfb_handle h, const float *psi, float *pres, size_t ref_x, size_t ref_y, float rho, float f)
 {
     if (!h || !psi || !pres) return fail(XFB_E_ARG, "null argument");
+    NO_SLAB(h, "xfb_invert_pres");
     const size_t ref = ref_x + (size_t)h->nx * ref_y;     // invert_pres.cpp:182 (x + XPTS*y, as written there)
     if (ref >= h->grids) return fail(XFB_E_ARG, "reference point out of range");
     CK(cudaSetDevice(h->device));

@@ -19,11 +19,11 @@ namespace xfb {
 enum { COL_FWD = 0, COL_INV = 1, COL_STEP = 2, COL_PRO = 3 };
 
 struct ColParams {
-    const cpx *jint;      // FWD/STEP: y-transformed lines [NX][pitch]
+    const cpx *jint;      // FWD/STEP: y-transformed lines, pair layout (see xfb_row.cuh): (i, j) at ((i>>1)*pitch + j)*2 + (i&1)
     cpx *z0;              // spectral state at the start of the step (FWD writes it)
     cpx *zk;              // stage state
     cpx *acc;             // running RK4 sum r1 + 2 r2 + 2 r3
-    cpx *t_out[4];        // x-inverse-transformed i kx Z, i ky Z, i ky Psi, i kx Psi ; INV: [0]
+    cpx *t_out[4];        // x-inverse-transformed i kx Z, i ky Z, i ky Psi, i kx Psi ; INV: [0]   (pair layout)
     const cpx *inv_in;    // INV: spectrum to transform
     const cpx *tw;
     int twn;
@@ -32,6 +32,7 @@ struct ColParams {
     const double *kx2;    // [NX]    (double)kx*kx
     const double *ky2;    // [pitch]
     int pitch;
+    int j_base;           // global index of this rank's first column (0 on one GPU): ky, mask and the (0,0) entry use it
     // layout of the K-COL-private state arrays z0/zk/acc: element (i, j0 + c) of column tile b lives at
     //   member_offset + b * st_tile_stride + i * st_row_stride + c
     // row-major (operator tier):  st_tile_stride = W,      st_row_stride = pitch
@@ -59,6 +60,13 @@ struct ColCfg {
     static constexpr int MINB = (THREADS <= 128) ? 4 : (THREADS <= 256) ? 2 : 1;
     static_assert(THREADS >= 16 && NIT <= 2, "bad column tile");
 };
+
+// element (i, j) of a pair-layout array (rows 2m, 2m+1 interleaved): ((i >> 1) * pitch + j) * 2 + (i & 1).
+// Rows i = t + k*G of one butterfly thread (G even) are k * G * pitch elements apart, as in a row-major array.
+__device__ __forceinline__ size_t pair_base(const int t, const int j, const int pitch)
+{
+    return ((size_t)(t >> 1) * (size_t)pitch + (size_t)j) * 2 + (size_t)(t & 1);
+}
 
 // -(kx^2 + ky^2) narrowed to float, summed in float64 like pow(float,2)+pow(float,2) (fftwfop.cpp:42-45)
 __device__ __forceinline__ float lap_coe(const double kx2, const double ky2) { return (float)(-(kx2 + ky2)); }
@@ -131,9 +139,9 @@ col_kernel(const ColParams p)
     if (MODE == COL_FWD || MODE == COL_STEP) {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            const cpx *src = p.jint + moff + j0 + c[it];
+            const cpx *src = p.jint + moff + pair_base(t[it], j0 + c[it], p.pitch);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) v[it][k] = __ldg(src + (size_t)(t[it] + k * G) * p.pitch);
+            for (int k = 0; k < 16; ++k) v[it][k] = __ldg(src + (size_t)(k * G) * p.pitch);
         }
         if (MODE == COL_STEP) {
             // the epilogue operands of this tile: start them towards L2 now, they are needed after the
@@ -150,7 +158,7 @@ col_kernel(const ColParams p)
         col_fft<NX, W, NIT>(v, sm, t, c, tw);
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            const int j = j0 + c[it];
+            const int j = p.j_base + j0 + c[it];
             const float kyv = __ldg(p.ky + j);
             const float ky2 = kyv * kyv;
             const size_t e0 = soff + (size_t)t[it] * srow + c[it];
@@ -224,9 +232,9 @@ col_kernel(const ColParams p)
         col_fft<NX, W, NIT>(v, sm, t, c, tw);
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            cpx *dst = p.t_out[0] + moff + j0 + c[it];
+            cpx *dst = p.t_out[0] + moff + pair_base(t[it], j0 + c[it], p.pitch);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) dst[(size_t)(t[it] + k * G) * p.pitch] = cswap(v[it][k]);
+            for (int k = 0; k < 16; ++k) dst[(size_t)(k * G) * p.pitch] = cswap(v[it][k]);
         }
     }
 
@@ -251,7 +259,7 @@ col_kernel(const ColParams p)
             }
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
-                const int j = j0 + c[it];
+                const int j = p.j_base + j0 + c[it];
                 const float ky = __ldg(p.ky + j);
                 const float ky2 = ky * ky;
 #pragma unroll
@@ -273,9 +281,9 @@ col_kernel(const ColParams p)
             cpx *outp = p.t_out[f];
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
-                cpx *dst = outp + moff + j0 + c[it];
+                cpx *dst = outp + moff + pair_base(t[it], j0 + c[it], p.pitch);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) dst[(size_t)(t[it] + k * G) * p.pitch] = cswap(v[it][k]);
+                for (int k = 0; k < 16; ++k) dst[(size_t)(k * G) * p.pitch] = cswap(v[it][k]);
             }
         }
     }

@@ -1,0 +1,569 @@
+// xfb_dist.cu -- slab decomposition of one large grid over the GPUs of a node (the
+// reference has no parallel path at all, src/main.cpp is one thread).
+//
+// Rank r of P holds the physical rows [r*NX/P, (r+1)*NX/P) and, in spectral space, a contiguous range of
+// columns.  A 2-D transform is   local 1-D pass -> all-to-all -> local 1-D pass;   per RK stage five
+// spectral arrays cross (the y-transformed tendency one way, the four x-inverse-transformed products the
+// other way).  K-ROW and K-COL are the single-GPU kernels: K-ROW addresses its spectral lines through
+// "panels" (one per (destination rank, column chunk), each a contiguous [rows][cw] block, so every
+// message of the all-to-all is one contiguous buffer), K-COL runs once per column chunk.
+//
+// Overlap: K-ROW is launched in row chunks and K-COL in column chunks; the exchange of chunk i runs on a
+// second stream while chunk i+1 computes, so only the last chunk's exchange is exposed.
+//
+// Two transports:
+//   NCCL     one process per GPU (xfb_create_dist): grouped ncclSend/ncclRecv over NVLink, libnccl.so.2 is
+//            loaded at run time (the single-GPU path does not depend on it);
+//   loopback all ranks in one process on ONE device sharing one stream (xfb_loopback_*): plain device
+//            copies.  It exists so the slab indexing is testable on a single GPU.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <new>
+
+#include "xfb_handle.h"
+
+namespace xfb {
+
+struct NcclApi {
+    void *lib;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    const char *(*GetErrorString)(ncclResult_t);
+};
+
+static NcclApi g_nccl;
+
+static int nccl_load()
+{
+    if (g_nccl.lib) return 0;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(XFB_E_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    NcclApi a;
+    a.lib = lib;
+#define SYM(field, name)                                                                   \
+    do {                                                                                   \
+        *(void **)(&a.field) = dlsym(lib, name);                                           \
+        if (!a.field) return fail(XFB_E_NCCL, "libnccl.so.2 has no symbol %s", name);      \
+    } while (0)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl = a;
+    return 0;
+}
+
+#define NCK(call)                                                                                        \
+    do {                                                                                                 \
+        ncclResult_t r__ = (call);                                                                       \
+        if (r__ != ncclSuccess) return fail(XFB_E_NCCL, "%s: %s", #call, g_nccl.GetErrorString(r__));    \
+    } while (0)
+
+struct Team {
+    int nranks;
+    int nlocal;               // loopback: nranks handles in this process; NCCL: 1
+    xfb_handle local[16];
+    ncclComm_t comm;          // NCCL transport
+    bool loopback;
+};
+
+// ---- block addressing -----------------------------------------------------------------------------
+// row side (K-ROW's panels): panel (q, c) = [rows][cw], rows paired ; col side (K-COL's chunks): chunk c = [NX][cw]
+static inline size_t row_off(xfb_handle h, int q, int c, int r0) { return ((size_t)(q * h->nchunks + c) * h->rows + r0) * h->pitch; }
+static inline size_t col_off(xfb_handle h, int q, int c, int r0) { return ((size_t)c * h->nx + (size_t)q * h->rows + r0) * h->pitch; }
+
+enum { ROW2COL = 0, COL2ROW = 1 };
+
+// One all-to-all of the blocks (column chunks [c0, c1), local rows [r0, r1)) of `na` arrays.
+// NCCL: issued for the single local rank on `st`.  Loopback: device copies for every rank on the shared stream.
+static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *col_ptrs_of_rank, int na, int c0, int c1, int r0,
+                    int r1, cudaStream_t st)
+{
+    // row_ptrs_of_rank / col_ptrs_of_rank: [nlocal][na]
+    xfb_handle h0 = T->local[0];
+    const size_t count = (size_t)(r1 - r0) * h0->pitch;      // complex elements per block
+    if (T->loopback) {
+        for (int R = 0; R < T->nranks; ++R)
+            for (int q = 0; q < T->nranks; ++q)
+                for (int a = 0; a < na; ++a)
+                    for (int c = c0; c < c1; ++c) {
+                        cpx *rowR = row_ptrs_of_rank[R * na + a], *colR = col_ptrs_of_rank[R * na + a];
+                        cpx *rowq = row_ptrs_of_rank[q * na + a], *colq = col_ptrs_of_rank[q * na + a];
+                        if (dir == ROW2COL)
+                            CK(cudaMemcpyAsync(colR + col_off(h0, q, c, r0), rowq + row_off(h0, R, c, r0), sizeof(cpx) * count,
+                                               cudaMemcpyDeviceToDevice, st));
+                        else
+                            CK(cudaMemcpyAsync(rowR + row_off(h0, q, c, r0), colq + col_off(h0, R, c, r0), sizeof(cpx) * count,
+                                               cudaMemcpyDeviceToDevice, st));
+                    }
+        return 0;
+    }
+    const int me = h0->rank;
+    NCK(g_nccl.GroupStart());
+    for (int a = 0; a < na; ++a)
+        for (int c = c0; c < c1; ++c)
+            for (int q = 0; q < T->nranks; ++q) {
+                cpx *row = row_ptrs_of_rank[a] + row_off(h0, q, c, r0), *col = col_ptrs_of_rank[a] + col_off(h0, q, c, r0);
+                const cpx *sendp = (dir == ROW2COL) ? row : col;
+                cpx *recvp = (dir == ROW2COL) ? col : row;
+                if (q == me) continue;
+                NCK(g_nccl.Send(sendp, 2 * count, ncclFloat, q, T->comm, st));
+                NCK(g_nccl.Recv(recvp, 2 * count, ncclFloat, q, T->comm, st));
+            }
+    NCK(g_nccl.GroupEnd());
+    for (int a = 0; a < na; ++a)
+        for (int c = c0; c < c1; ++c) {
+            cpx *row = row_ptrs_of_rank[a] + row_off(h0, me, c, r0), *col = col_ptrs_of_rank[a] + col_off(h0, me, c, r0);
+            CK(cudaMemcpyAsync((dir == ROW2COL) ? col : row, (dir == ROW2COL) ? row : col, sizeof(cpx) * count,
+                               cudaMemcpyDeviceToDevice, st));
+        }
+    return 0;
+}
+
+// ---- per-rank launches --------------------------------------------------------------------------------
+static int launch_row_chunk(xfb_handle h, int mode, const cpx *const in[4], const float *real_in, cpx *spec_out, float *real_out,
+                            int negate, int r0, int r1)
+{
+    RowParams r;
+    fill_row(h, r, r1 - r0);
+    const size_t so = (size_t)r0 * h->pitch, ro = (size_t)r0 * h->ny;
+    for (int f = 0; f < 4; ++f) r.spec_in[f] = in && in[f] ? in[f] + so : nullptr;
+    r.real_in = real_in ? real_in + ro : nullptr;
+    r.spec_out = spec_out ? spec_out + so : nullptr;
+    r.real_out = real_out ? real_out + ro : nullptr;
+    r.negate = negate;
+    CKL(h, launch_row(h->ny, mode, r, h->stream));
+    return 0;
+}
+
+static int launch_col_chunk(xfb_handle h, int mode, int chunk, int stage, float dt, const cpx *inv_in, cpx *inv_out)
+{
+    ColParams c;
+    fill_col(h, c, chunk);
+    const size_t off = (size_t)chunk * h->nx * h->pitch;
+    c.jint = h->jint_recv + off; c.z0 = h->z0 + off; c.zk = h->zk + off; c.acc = h->acc + off;
+    c.st_tile_stride = (long long)h->nx * h->tw_state; c.st_row_stride = h->tw_state;     // tile-major state
+    for (int f = 0; f < 4; ++f) c.t_out[f] = h->t[f] + off;
+    if (mode == COL_INV) { c.inv_in = inv_in + off; c.t_out[0] = inv_out + off; }
+    c.dt = dt; c.stage = stage;
+    c.dt_stage = (stage == 3) ? dt : dt / 2.0f;          // main.cpp:296,299,302
+    CKL(h, launch_col(h->nx, mode, c, 1, h->stream));
+    return 0;
+}
+
+// events around the exchanges when profiling (NCCL transport only; the loopback shares the compute stream)
+static void a2a_mark(xfb_handle h, cudaStream_t st)
+{
+    if (h->profiling && h->ev_a2a) cudaEventRecord(next_event(h->ev_a2a, h->ev_a2a_used), st);
+}
+
+// y pass for all local ranks (row chunks) + exchange into the column side.
+//   produce(h, r0, r1) launches K-ROW on local rows [r0, r1) ; row_of(h) / col_of(h) name the two arrays
+template <typename F, typename GR, typename GC>
+static int rows_then_exchange(Team *T, F produce, GR row_of, GC col_of)
+{
+    xfb_handle h0 = T->local[0];
+    const int C = h0->nchunks, rc = h0->rows / C;
+    cpx *rp[16], *cp[16];
+    for (int l = 0; l < T->nlocal; ++l) { rp[l] = row_of(T->local[l]); cp[l] = col_of(T->local[l]); }
+    if (T->loopback) {
+        for (int l = 0; l < T->nlocal; ++l)
+            for (int i = 0; i < C; ++i)
+                if (int e = produce(T->local[l], i * rc, (i + 1) * rc)) return e;
+        return exchange(T, ROW2COL, rp, cp, 1, 0, C, 0, h0->rows, h0->stream);
+    }
+    for (int i = 0; i < C; ++i) {
+        if (int e = produce(h0, i * rc, (i + 1) * rc)) return e;
+        CK(cudaEventRecord(h0->ev_chunk[i], h0->stream));
+        CK(cudaStreamWaitEvent(h0->comm_stream, h0->ev_chunk[i], 0));
+        a2a_mark(h0, h0->comm_stream);
+        if (int e = exchange(T, ROW2COL, rp, cp, 1, 0, C, i * rc, (i + 1) * rc, h0->comm_stream)) return e;
+        a2a_mark(h0, h0->comm_stream);
+    }
+    CK(cudaEventRecord(h0->ev_comm[0], h0->comm_stream));
+    CK(cudaStreamWaitEvent(h0->stream, h0->ev_comm[0], 0));
+    return 0;
+}
+
+// x pass for all local ranks (column chunks) + exchange of `na` arrays back to the row side.
+//   produce(h, chunk) launches K-COL ; col_of(h, a) / row_of(h, a) name array a on the two sides
+template <typename F, typename GC, typename GR>
+static int cols_then_exchange(Team *T, F produce, GC col_of, GR row_of, int na)
+{
+    xfb_handle h0 = T->local[0];
+    const int C = h0->nchunks;
+    cpx *rp[16 * 4], *cp[16 * 4];
+    for (int l = 0; l < T->nlocal; ++l)
+        for (int a = 0; a < na; ++a) { rp[l * na + a] = row_of(T->local[l], a); cp[l * na + a] = col_of(T->local[l], a); }
+    if (T->loopback) {
+        for (int l = 0; l < T->nlocal; ++l)
+            for (int c = 0; c < C; ++c)
+                if (int e = produce(T->local[l], c)) return e;
+        return exchange(T, COL2ROW, rp, cp, na, 0, C, 0, h0->rows, h0->stream);
+    }
+    for (int c = 0; c < C; ++c) {
+        if (int e = produce(h0, c)) return e;
+        CK(cudaEventRecord(h0->ev_chunk[c], h0->stream));
+        CK(cudaStreamWaitEvent(h0->comm_stream, h0->ev_chunk[c], 0));
+        a2a_mark(h0, h0->comm_stream);
+        if (int e = exchange(T, COL2ROW, rp, cp, na, c, c + 1, 0, h0->rows, h0->comm_stream)) return e;
+        a2a_mark(h0, h0->comm_stream);
+    }
+    CK(cudaEventRecord(h0->ev_comm[1], h0->comm_stream));
+    CK(cudaStreamWaitEvent(h0->stream, h0->ev_comm[1], 0));
+    return 0;
+}
+
+// ---- team-level operations ------------------------------------------------------------------------------
+// vort[l]: device pointer to the local rows of rank local[l]
+static int team_set_vorticity(Team *T, const float *const *vort)
+{
+    int e = rows_then_exchange(
+        T,
+        [&](xfb_handle h, int r0, int r1) {
+            int l = 0;
+            while (T->local[l] != h) ++l;
+            return launch_row_chunk(h, ROW_R2C, nullptr, vort[l], h->jint, nullptr, 0, r0, r1);
+        },
+        [](xfb_handle h) { return h->jint; }, [](xfb_handle h) { return h->jint_recv; });
+    if (e) return e;
+    for (int l = 0; l < T->nlocal; ++l) {
+        xfb_handle h = T->local[l];
+        for (int c = 0; c < h->nchunks; ++c)
+            if (int e2 = launch_col_chunk(h, COL_FWD, c, 0, 0.f, nullptr, nullptr)) return e2;
+        h->have_state = true;
+        h->tf_valid = false;
+    }
+    return 0;
+}
+
+static int team_products(Team *T, int mode, int stage, float dt)
+{
+    return cols_then_exchange(
+        T, [&](xfb_handle h, int c) { return launch_col_chunk(h, mode, c, stage, dt, nullptr, nullptr); },
+        [](xfb_handle h, int a) { return h->t[a]; }, [](xfb_handle h, int a) { return h->tr[a]; }, 4);
+}
+
+static int team_step(Team *T, int nsteps, float dt)
+{
+    xfb_handle h0 = T->local[0];
+    if (nsteps > 0 && !h0->tf_valid) {
+        if (int e = team_products(T, COL_PRO, 0, dt)) return e;
+        for (int l = 0; l < T->nlocal; ++l) T->local[l]->tf_valid = true;
+    }
+    for (int s = 0; s < nsteps; ++s)
+        for (int k = 1; k <= 4; ++k) {
+            if (h0->profiling && !T->loopback) cudaEventRecord(next_event(h0->ev_row, h0->ev_row_used), h0->stream);
+            int e = rows_then_exchange(
+                T,
+                [&](xfb_handle h, int r0, int r1) {
+                    return launch_row_chunk(h, ROW_JAC, h->tr, h->has_src ? h->src : nullptr, h->jint, nullptr, 0, r0, r1);
+                },
+                [](xfb_handle h) { return h->jint; }, [](xfb_handle h) { return h->jint_recv; });
+            if (e) return e;
+            if (h0->profiling && !T->loopback) {
+                cudaEventRecord(next_event(h0->ev_row, h0->ev_row_used), h0->stream);
+                cudaEventRecord(next_event(h0->ev_col, h0->ev_col_used), h0->stream);
+            }
+            if (int e2 = team_products(T, COL_STEP, k, dt)) return e2;
+            if (h0->profiling && !T->loopback) cudaEventRecord(next_event(h0->ev_col, h0->ev_col_used), h0->stream);
+        }
+    return 0;
+}
+
+__global__ void dist_diag_kernel(const float *pxy, const float *pxx, const float *pyy, float *out, long long n, int which)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float s1 = __fmul_rn(-2.0f, pxy[i]), s2 = __fsub_rn(pxx[i], pyy[i]), z = __fadd_rn(pxx[i], pyy[i]);
+    const float ss = __fadd_rn(__fmul_rn(s1, s1), __fmul_rn(s2, s2)), zz = __fmul_rn(z, z);
+    const float q = __fsub_rn(ss, zz), den = __fadd_rn(ss, zz);
+    if (which == XFB_TFIL) out[i] = (q > 0.0f) ? __fdiv_rn(2.0f, __fsqrt_rn(q)) : 0.0f;
+    else out[i] = (den > 0.0f) ? __fdiv_rn(q, den) : 0.0f;
+}
+
+// spectral operator chain `ops` applied to the state, inverse 2-D transform, into dout[l] (device, local rows)
+static int team_inverse(Team *T, const int *ops, int nops, int negate, float *const *dout)
+{
+    int e = cols_then_exchange(
+        T,
+        [&](xfb_handle h, int c) {
+            const size_t off = (size_t)c * h->nx * h->pitch;
+            const int P = h->pitch;
+            if (launch_pw(h, ops[0], h->z0 + off, P, h->spec_a + off, P, P, h->tw_state, 0, c)) return (int)XFB_E_CUDA;
+            for (int o = 1; o < nops; ++o)
+                if (launch_pw(h, ops[o], h->spec_a + off, P, h->spec_a + off, P, P, 0, 0, c)) return (int)XFB_E_CUDA;
+            return launch_col_chunk(h, COL_INV, c, 0, 0.f, h->spec_a, h->spec_b);
+        },
+        [](xfb_handle h, int) { return h->spec_b; }, [](xfb_handle h, int) { return h->tr[0]; }, 1);
+    if (e) return e;
+    for (int l = 0; l < T->nlocal; ++l) {
+        xfb_handle h = T->local[l];
+        const cpx *in[4] = {h->tr[0], nullptr, nullptr, nullptr};
+        if (int e2 = launch_row_chunk(h, ROW_C2R, in, nullptr, nullptr, dout[l], negate, 0, h->rows)) return e2;
+        h->tf_valid = false;                      // tr[0] was scratch
+    }
+    return 0;
+}
+
+static int team_get_field(Team *T, int which, float *const *dout)
+{
+    static const int op_vort[] = {OP_COPY}, op_psi[] = {OP_INVLAP}, op_u[] = {OP_INVLAP, OP_GRADY}, op_v[] = {OP_INVLAP, OP_GRADX},
+                     op_zx[] = {OP_GRADX}, op_zy[] = {OP_GRADY}, op_pxy[] = {OP_INVLAP, OP_GRADX, OP_GRADY},
+                     op_pxx[] = {OP_INVLAP, OP_GRADX, OP_GRADX}, op_pyy[] = {OP_INVLAP, OP_GRADY, OP_GRADY};
+    switch (which) {
+    case XFB_VORT: return team_inverse(T, op_vort, 1, 0, dout);
+    case XFB_PSI: return team_inverse(T, op_psi, 1, 0, dout);
+    case XFB_U: return team_inverse(T, op_u, 2, 1, dout);
+    case XFB_V: return team_inverse(T, op_v, 2, 0, dout);
+    case XFB_DVORTDX: return team_inverse(T, op_zx, 1, 0, dout);
+    case XFB_DVORTDY: return team_inverse(T, op_zy, 1, 0, dout);
+    case XFB_TFIL:
+    case XFB_DEFORM: {
+        float *b[16], *c[16];
+        for (int l = 0; l < T->nlocal; ++l) { b[l] = T->local[l]->real_b; c[l] = T->local[l]->real_c; }
+        if (int e = team_inverse(T, op_pxy, 3, 0, b)) return e;
+        if (int e = team_inverse(T, op_pxx, 3, 0, c)) return e;
+        if (int e = team_inverse(T, op_pyy, 3, 0, dout)) return e;
+        for (int l = 0; l < T->nlocal; ++l) {
+            xfb_handle h = T->local[l];
+            const long long n = (long long)h->grids;
+            dist_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(b[l], c[l], dout[l], dout[l], n, which);
+            CK(cudaGetLastError());
+            h->launches++;
+        }
+        return 0;
+    }
+    }
+    return fail(XFB_E_ARG, "bad field id %d", which);
+}
+
+// ---- entry points used by xfb_api.cu for NCCL handles ----------------------------------------------------
+int dist_set_vorticity(xfb_handle h, const float *vort_rows)
+{
+    if (h->team->loopback) return fail(XFB_E_STATE, "loopback ranks are driven through xfb_loopback_*");
+    const float *din = vort_rows;
+    if (!is_device_ptr(vort_rows)) {
+        CK(cudaMemcpyAsync(h->real_a, vort_rows, sizeof(float) * h->grids, cudaMemcpyHostToDevice, h->stream));
+        din = h->real_a;
+    }
+    if (int e = team_set_vorticity(h->team, &din)) return e;
+    if (!is_device_ptr(vort_rows)) CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int dist_step(xfb_handle h, int nsteps, float dt)
+{
+    if (h->team->loopback) return fail(XFB_E_STATE, "loopback ranks are driven through xfb_loopback_*");
+    return team_step(h->team, nsteps, dt);
+}
+
+int dist_get_field(xfb_handle h, int which, float *out_rows)
+{
+    if (h->team->loopback) return fail(XFB_E_STATE, "loopback ranks are driven through xfb_loopback_*");
+    float *dout = is_device_ptr(out_rows) ? out_rows : h->real_a;
+    if (int e = team_get_field(h->team, which, &dout)) return e;
+    if (dout != out_rows) {
+        CK(cudaMemcpyAsync(out_rows, dout, sizeof(float) * h->grids, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+void dist_release(xfb_handle h)
+{
+    Team *T = h->team;
+    if (!T) return;
+    if (T->loopback) return;                      // owned by xfb_loopback_destroy
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->comm_stream);
+    if (T->comm) g_nccl.CommDestroy(T->comm);
+    delete T;
+    h->team = nullptr;
+    destroy_impl(h);
+}
+
+}  // namespace xfb
+
+using namespace xfb;
+
+// ---- C ABI ---------------------------------------------------------------------------------------------------
+extern "C" int xfb_nccl_unique_id(char *id128)
+{
+    if (!id128) return fail(XFB_E_ARG, "null id buffer");
+    if (nccl_load()) return XFB_E_NCCL;
+    ncclUniqueId id;
+    NCK(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+extern "C" int xfb_create_dist(xfb_handle *out, int nx, int ny, float lx, float ly, float nu, int device, int rank, int nranks,
+                               int nchunks, const char *id128)
+{
+    if (!out) return fail(XFB_E_ARG, "null handle pointer");
+    if (nranks == 1) return create_impl(out, nx, ny, lx, ly, nu, 1, device, 0, 1, 1);
+    if (!id128) return fail(XFB_E_ARG, "xfb_create_dist: null unique id");
+    if (nranks > 16) return fail(XFB_E_ARG, "xfb_create_dist: at most 16 ranks");
+    if (nccl_load()) return XFB_E_NCCL;
+    if (int e = create_impl(out, nx, ny, lx, ly, nu, 1, device, rank, nranks, nchunks)) return e;
+    xfb_handle h = *out;
+    if ((h->rows / nchunks) % 2 != 0 || h->rows % nchunks != 0) {
+        destroy_impl(h);
+        *out = nullptr;
+        return fail(XFB_E_SIZE, "xfb_create_dist: %d local rows do not split into %d even chunks", h->rows, nchunks);
+    }
+    Team *T = new (std::nothrow) Team();
+    if (!T) return fail(XFB_E_ARG, "out of host memory");
+    memset(T, 0, sizeof(*T));
+    T->nranks = nranks; T->nlocal = 1; T->local[0] = h; T->loopback = false;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&T->comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        delete T;
+        destroy_impl(h);
+        *out = nullptr;
+        return fail(XFB_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    }
+    h->team = T;
+    h->ev_a2a = new std::vector<cudaEvent_t>();
+    return 0;
+}
+
+extern "C" int xfb_profile_read_a2a(xfb_handle h, double *a2a_ms, long long *exchanges)
+{
+    if (!h || !a2a_ms || !exchanges) return fail(XFB_E_ARG, "null argument");
+    *a2a_ms = 0.0;
+    *exchanges = 0;
+    if (!h->ev_a2a) return 0;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaStreamSynchronize(h->comm_stream));
+    *exchanges = (long long)(h->ev_a2a_used / 2);
+    for (size_t i = 0; i + 1 < h->ev_a2a_used; i += 2) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, (*h->ev_a2a)[i], (*h->ev_a2a)[i + 1]));
+        *a2a_ms += ms;
+    }
+    return 0;
+}
+
+// ---- loopback team: all ranks in this process on one device (slab indexing testable on a single GPU) ------
+struct xfb_loopback_s {
+    Team team;
+    int nx, ny;
+    float *full;             // device scratch, one full field
+};
+
+extern "C" int xfb_loopback_create(xfb_loopback_s **out, int nx, int ny, float lx, float ly, float nu, int device, int nranks,
+                                   int nchunks)
+{
+    if (!out) return fail(XFB_E_ARG, "null pointer");
+    *out = nullptr;
+    if (nranks < 2 || nranks > 16) return fail(XFB_E_ARG, "xfb_loopback_create: 2..16 ranks");
+    xfb_loopback_s *L = new (std::nothrow) xfb_loopback_s();
+    if (!L) return fail(XFB_E_ARG, "out of host memory");
+    memset(L, 0, sizeof(*L));
+    L->nx = nx; L->ny = ny;
+    L->team.nranks = nranks; L->team.nlocal = nranks; L->team.loopback = true;
+    for (int r = 0; r < nranks; ++r) {
+        xfb_handle h;
+        if (int e = create_impl(&h, nx, ny, lx, ly, nu, 1, device, r, nranks, nchunks)) return e;
+        if (h->rows % nchunks != 0 || (h->rows / nchunks) % 2 != 0)
+            return fail(XFB_E_SIZE, "xfb_loopback_create: %d local rows do not split into %d even chunks", h->rows, nchunks);
+        // every rank works on rank 0's stream: program order is the only synchronisation needed
+        if (r > 0) {
+            cudaStreamDestroy(h->stream);
+            h->stream = L->team.local[0]->stream;
+        }
+        h->team = &L->team;
+        L->team.local[r] = h;
+    }
+    if (dev_alloc((void **)&L->full, sizeof(float) * (size_t)nx * ny)) return XFB_E_CUDA;
+    *out = L;
+    return 0;
+}
+
+extern "C" int xfb_loopback_destroy(xfb_loopback_s *L)
+{
+    if (!L) return 0;
+    cudaStreamSynchronize(L->team.local[0]->stream);
+    for (int r = L->team.nranks - 1; r >= 0; --r) {
+        xfb_handle h = L->team.local[r];
+        h->team = nullptr;
+        if (r > 0) CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));   // give it back a stream of its own to destroy
+        destroy_impl(h);
+    }
+    cudaFree(L->full);
+    delete L;
+    return 0;
+}
+
+extern "C" int xfb_loopback_set_vorticity(xfb_loopback_s *L, const float *vort_full_host)
+{
+    if (!L || !vort_full_host) return fail(XFB_E_ARG, "null argument");
+    xfb_handle h0 = L->team.local[0];
+    CK(cudaSetDevice(h0->device));
+    CK(cudaMemcpyAsync(L->full, vort_full_host, sizeof(float) * (size_t)L->nx * L->ny, cudaMemcpyHostToDevice, h0->stream));
+    const float *rows[16];
+    for (int r = 0; r < L->team.nranks; ++r) rows[r] = L->full + (size_t)r * h0->rows * L->ny;
+    if (int e = team_set_vorticity(&L->team, rows)) return e;
+    CK(cudaStreamSynchronize(h0->stream));
+    return 0;
+}
+
+extern "C" int xfb_loopback_set_source(xfb_loopback_s *L, const float *src_full_host)
+{
+    if (!L) return fail(XFB_E_ARG, "null argument");
+    for (int r = 0; r < L->team.nranks; ++r) {
+        xfb_handle h = L->team.local[r];
+        if (int e = xfb_set_source(h, 0, src_full_host ? src_full_host + (size_t)r * h->rows * L->ny : nullptr)) return e;
+    }
+    return 0;
+}
+
+extern "C" int xfb_loopback_step(xfb_loopback_s *L, int nsteps, float dt)
+{
+    if (!L) return fail(XFB_E_ARG, "null argument");
+    if (!L->team.local[0]->have_state) return fail(XFB_E_STATE, "xfb_loopback_step before xfb_loopback_set_vorticity");
+    CK(cudaSetDevice(L->team.local[0]->device));
+    return team_step(&L->team, nsteps, dt);
+}
+
+extern "C" int xfb_loopback_get_field(xfb_loopback_s *L, int which, float *out_full_host)
+{
+    if (!L || !out_full_host) return fail(XFB_E_ARG, "null argument");
+    xfb_handle h0 = L->team.local[0];
+    if (!h0->have_state) return fail(XFB_E_STATE, "xfb_loopback_get_field before xfb_loopback_set_vorticity");
+    CK(cudaSetDevice(h0->device));
+    float *rows[16];
+    for (int r = 0; r < L->team.nranks; ++r) rows[r] = L->full + (size_t)r * h0->rows * L->ny;
+    if (int e = team_get_field(&L->team, which, rows)) return e;
+    CK(cudaMemcpyAsync(out_full_host, L->full, sizeof(float) * (size_t)L->nx * L->ny, cudaMemcpyDeviceToHost, h0->stream));
+    CK(cudaStreamSynchronize(h0->stream));
+    return 0;
+}
+
+extern "C" long long xfb_loopback_launch_count(xfb_loopback_s *L)
+{
+    long long n = 0;
+    if (L)
+        for (int r = 0; r < L->team.nranks; ++r) n += L->team.local[r]->launches;
+    return n;
+}

@@ -262,11 +262,29 @@ __device__ __forceinline__ void rem_pass(cpx (&v)[16], const LineTw<L> &tw)
     }
 }
 
+// Barriers.  A CTA that transforms several independent lines gives each line its own named barrier so the
+// lines do not wait for one another (they behave like separate CTAs sharing one SM's shared memory).
+struct CtaBar {
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+struct NamedBar {
+    int id, nthreads;      // id 1..4 (immediate barrier names keep the CTA's barrier allocation small), nthreads % 32 == 0
+    __device__ __forceinline__ void sync() const
+    {
+        switch (id) {
+        case 1: asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); break;
+        case 2: asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); break;
+        case 3: asm volatile("bar.sync 3, %0;" ::"r"(nthreads) : "memory"); break;
+        default: asm volatile("bar.sync 4, %0;" ::"r"(nthreads) : "memory"); break;
+        }
+    }
+};
+
 // Forward FFT of one line held as v[k] = x[t + k*G].  `sm` points at this line's padded
 // shared buffer; element address = (padpos(pos) * W + c).  All threads of the CTA must call
 // this together (it uses __syncthreads()).  On return v[k] = X[t + k*G].
-template <int L, int W>
-__device__ __forceinline__ void line_fft(cpx (&v)[16], cpx *sm, const int t, const int c, const LineTw<L> &tw)
+template <int L, int W, typename Bar>
+__device__ __forceinline__ void line_fft(cpx (&v)[16], cpx *sm, const int t, const int c, const LineTw<L> &tw, const Bar &bar)
 {
     typedef LinePlan<L> P;
     int ns = 1;
@@ -275,9 +293,9 @@ __device__ __forceinline__ void line_fft(cpx (&v)[16], cpx *sm, const int t, con
         pass16_compute<L>(v, p, tw);
         if (p != P::NPASS - 1) {
             exchange_write<W>(v, sm, t, c, ns);
-            __syncthreads();
+            bar.sync();
             exchange_read<P::G, W>(v, sm, t, c);
-            __syncthreads();
+            bar.sync();
         }
         ns *= 16;
     }

@@ -1,0 +1,97 @@
+// xfb_handle.h -- the handle behind the C ABI and the helpers shared by xfb_api.cu (single GPU) and
+// xfb_dist.cu (slab decomposition).
+#pragma once
+#include <cstdarg>
+#include <cstddef>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/xfb.h"
+#include "xfb_internal.h"
+
+namespace xfb {
+
+int fail(int code, const char *fmt, ...);
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) return xfb::fail(XFB_E_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define CKL(h, call)                                                                                         \
+    do {                                                                                                     \
+        int e__ = (call);                                                                                    \
+        if (e__ != 0) return xfb::fail(XFB_E_CUDA, "%s: %s", #call, cudaGetErrorString((cudaError_t)e__));   \
+        (h)->launches++;                                                                                     \
+    } while (0)
+
+struct Team;
+
+}  // namespace xfb
+
+struct xfb_handle_s {
+    int nx, ny, hy, pitch, batch, device;
+    int tw_state;        // column tile width = tile-major layout of z0/zk/acc
+    float lx, ly, nu;
+    // per member: real points held (rows * ny), reference half spectrum nx*(ny/2+1), padded spectral array
+    size_t grids, hgrids, hpad;
+    cudaStream_t stream;
+    // tables
+    xfb::cpx *tw;
+    int twn;
+    float *kx, *ky;
+    double *kx2, *ky2;
+    double mask_kd;
+    // stepper state (per member one padded array)
+    xfb::cpx *z0, *zk, *acc, *jint, *t[4];
+    float *src;          // [batch][rows][ny], allocated on first use
+    bool has_src;
+    bool have_state;     // a vorticity/spectrum has been set
+    bool tf_valid;       // t[0..3] hold the prologue of the current z0
+    // scratch for the operator tier / record path (one member)
+    float *real_a, *real_b, *real_c;
+    xfb::cpx *spec_a, *spec_b;      // padded layout
+    float *ref_a, *ref_b;           // reference layout half spectra (2*hgrids floats)
+    long long launches;
+    // ---- slab decomposition (xfb_dist.cu); nranks == 1 otherwise ------------------------------------
+    // rank r holds physical rows [r*rows, (r+1)*rows) and the spectral columns of panels r*nchunks ..
+    // (r+1)*nchunks-1; a panel is `pitch` (= cw) columns wide, pitch_g = pitch * nranks * nchunks.
+    int rank, nranks, rows, nchunks, pitch_g, col0;
+    unsigned cw_magic;
+    xfb::Team *team;
+    xfb::cpx *jint_recv, *tr[4];    // receive sides of the two transposes
+    cudaStream_t comm_stream;
+    cudaEvent_t ev_chunk[16], ev_comm[2];
+    // optional per-kernel timing (xfb_profile)
+    bool profiling;
+    std::vector<cudaEvent_t> *ev_row, *ev_col, *ev_a2a;   // pairs (begin, end)
+    size_t ev_row_used, ev_col_used, ev_a2a_used;
+};
+
+namespace xfb {
+
+cudaEvent_t next_event(std::vector<cudaEvent_t> *pool, size_t &used);
+int dev_alloc(void **p, size_t bytes);
+bool is_device_ptr(const void *p);
+
+enum { OP_GRADX = 0, OP_GRADY = 1, OP_LAP = 2, OP_INVLAP = 3, OP_DEALIAS = 4, OP_COPY = 5 };
+
+// pointwise spectral operator on one chunk of K-COL-side columns (chunk 0 on one GPU)
+int launch_pw(xfb_handle h, int op, const cpx *in, int in_pitch, cpx *out, int out_pitch, int ncols, int in_tw = 0,
+              int out_tw = 0, int chunk = 0);
+void fill_row(xfb_handle h, RowParams &p, int nrows);
+void fill_col(xfb_handle h, ColParams &p, int chunk = 0);
+
+// common part of xfb_create / xfb_create_dist / the loopback team
+int create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float nu, int batch, int device, int rank, int nranks,
+                int nchunks);
+int destroy_impl(xfb_handle h);
+
+// slab paths (xfb_dist.cu)
+int dist_set_vorticity(xfb_handle h, const float *vort_rows);
+int dist_step(xfb_handle h, int nsteps, float dt);
+int dist_get_field(xfb_handle h, int which, float *out_rows);
+void dist_release(xfb_handle h);
+
+}  // namespace xfb

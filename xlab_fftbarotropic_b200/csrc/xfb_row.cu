@@ -11,29 +11,30 @@ bool row_size_ok(int ny)
     }
 }
 
-template <int NY, int MODE>
+template <int NY, int MODE, bool DIST>
 static int launch_row_t(const RowParams &p, cudaStream_t st)
 {
     typedef RowCfg<NY> C;
     constexpr int smem = (MODE == ROW_JAC) ? C::SMEM_JAC : C::SMEM;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(row_kernel<NY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(row_kernel<NY, MODE, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     const int blocks = (p.nrows + C::LPC - 1) / C::LPC;
-    row_kernel<NY, MODE><<<blocks, C::THREADS, smem, st>>>(p);
+    row_kernel<NY, MODE, DIST><<<blocks, C::THREADS, smem, st>>>(p);
     return (int)cudaGetLastError();
 }
 
 template <int NY>
 static int launch_row_n(int mode, const RowParams &p, cudaStream_t st)
 {
+    const bool dist = p.cw > 0;
     switch (mode) {
-    case ROW_R2C: return launch_row_t<NY, ROW_R2C>(p, st);
-    case ROW_C2R: return launch_row_t<NY, ROW_C2R>(p, st);
-    case ROW_JAC: return launch_row_t<NY, ROW_JAC>(p, st);
+    case ROW_R2C: return dist ? launch_row_t<NY, ROW_R2C, true>(p, st) : launch_row_t<NY, ROW_R2C, false>(p, st);
+    case ROW_C2R: return dist ? launch_row_t<NY, ROW_C2R, true>(p, st) : launch_row_t<NY, ROW_C2R, false>(p, st);
+    case ROW_JAC: return dist ? launch_row_t<NY, ROW_JAC, true>(p, st) : launch_row_t<NY, ROW_JAC, false>(p, st);
     }
     return (int)cudaErrorInvalidValue;
 }

@@ -8,6 +8,14 @@
 //         registers -- the physical-space fields never touch HBM.
 // A real line of NY points is transformed as a complex line of L = NY/2 points plus the
 // standard split/merge step of a half-length real transform.
+//
+// Layout of the spectral lines exchanged with K-COL ("pair layout"): rows 2m and 2m+1 are interleaved
+// element by element, element (i, k) lives at ((i >> 1) * pitch + k) * 2 + (i & 1).  K-COL reads and writes
+// these arrays in tiles of W columns x all rows; with the rows paired a W = 2 tile touches whole 32-byte
+// sectors (2 columns x 2 rows) instead of half sectors -- measured 4.8 TB/s against 1.9 TB/s for a plain
+// strided tile copy on B200 (tools/probes/probe_tma_tile.cu).  The two lines of a pair are transformed by
+// the same CTA whenever a CTA holds more than one line, so the half-used sectors of one line are L1 hits
+// of the other.
 #pragma once
 #include "xfb_fft.cuh"
 
@@ -24,6 +32,12 @@ struct RowParams {
     int twn;
     int nrows;               // NX * batch
     int pitch;               // complex elements per spectral line (>= NY/2+1)
+    // slab-decomposed runs (DIST): a spectral line is cut into `pitch / cw` panels of cw columns, one per
+    // (rank, column chunk); element k of local row r lives at
+    //   (k / cw) * panel_stride + ((r >> 1) * cw + (k % cw)) * 2 + (r & 1)
+    int cw;                  // columns per panel
+    long long panel_stride;  // complex elements between panels (= local rows * cw)
+    unsigned cw_magic;       // ceil(2^32 / cw): k / cw == __umulhi(k, cw_magic) for every k < pitch (checked on the host)
     float scale;             // 1/(NX*NY) applied after every C2R (fftwf_backward_normalize)
     int negate;              // C2R: multiply by -1 after scaling (u = -u)
 };
@@ -32,7 +46,8 @@ template <int NY>
 struct RowCfg {
     static constexpr int L = NY / 2;
     static constexpr int G = L / 16;                         // threads per line
-    static constexpr int THREADS = (G >= 128) ? G : 128;
+    // both lines of a row pair in one CTA wherever the shared memory allows it (NY <= 8192)
+    static constexpr int THREADS = (G >= 512) ? G : (2 * G >= 128) ? 2 * G : 128;
     static constexpr int LPC = THREADS / G;                  // lines per CTA
     static constexpr int SMEM = LPC * LinePlan<L>::PADDED * (int)sizeof(cpx);
     // JAC parks -u (then -u * dvortdx) and v in shared memory between the four inverse transforms, so
@@ -40,6 +55,32 @@ struct RowCfg {
     static constexpr int SMEM_JAC = SMEM + 2 * LPC * L * (int)sizeof(cpx);
     static constexpr int MINB = (THREADS >= 512) ? 1 : (THREADS >= 256) ? 2 : 4;
 };
+
+template <bool NAMED>
+struct RowBarSel {
+    typedef CtaBar type;
+    static __device__ __forceinline__ CtaBar make(int, int) { return CtaBar(); }
+};
+template <>
+struct RowBarSel<true> {
+    typedef NamedBar type;
+    static __device__ __forceinline__ NamedBar make(int id, int n) { return NamedBar{id, n}; }
+};
+
+// position of element k of a spectral line relative to the line's base pointer (pair layout: stride 2)
+template <bool DIST>
+__device__ __forceinline__ long long line_pos(const RowParams &p, const int k)
+{
+    if (!DIST) return 2 * k;
+    const int panel = (int)__umulhi((unsigned)k, p.cw_magic);
+    return (long long)panel * p.panel_stride + 2 * (k - panel * p.cw);
+}
+
+// base of the line of `row` in a pair-layout array whose rows hold `rowpitch` complex elements
+__device__ __forceinline__ size_t line_base(const int row, const int rowpitch)
+{
+    return (size_t)(row >> 1) * (size_t)(2 * rowpitch) + (size_t)(row & 1);
+}
 
 // exp(-2 pi i q / 32), q = 0..15
 __device__ __forceinline__ cpx w32(int q)
@@ -56,9 +97,9 @@ __device__ __forceinline__ cpx w32(int q)
 
 // half-spectrum line X[0..L] -> physical pairs: on return v[q] = (x[2m+1], x[2m]) * 1 (unscaled,
 // swapped), m = t + q*G.  wt = exp(-2 pi i t / NY).
-template <int NY>
-__device__ __forceinline__ void c2r_line(cpx (&v)[16], const cpx *X, cpx *sm, int t, cpx wt,
-                                         const LineTw<NY / 2> &tw)
+template <int NY, bool DIST, typename Bar>
+__device__ __forceinline__ void c2r_line(cpx (&v)[16], const cpx *X, const RowParams &p, cpx *sm, int t, cpx wt,
+                                         const LineTw<NY / 2> &tw, const Bar &bar)
 {
     constexpr int L = NY / 2, G = L / 16;
     wt = launder(wt);
@@ -68,8 +109,8 @@ __device__ __forceinline__ void c2r_line(cpx (&v)[16], const cpx *X, cpx *sm, in
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int k = t + (8 * h + e) * G;
-            a[e] = X[k];
-            b[e] = X[L - k];
+            a[e] = X[line_pos<DIST>(p, k)];
+            b[e] = X[line_pos<DIST>(p, L - k)];
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -84,20 +125,20 @@ __device__ __forceinline__ void c2r_line(cpx (&v)[16], const cpx *X, cpx *sm, in
             v[q] = mk(E.y + O.x, E.x - O.y);
         }
     }
-    line_fft<L, 1>(v, sm, t, 0, tw);
+    line_fft<L, 1>(v, sm, t, 0, tw, bar);
 }
 
 // physical pairs v[q] = (x[2m], x[2m+1]) -> half-spectrum line written to Xout[0..L] (+ zeroed pad)
-template <int NY>
-__device__ __forceinline__ void r2c_line(cpx (&v)[16], cpx *__restrict__ Xout, int pitch, cpx *sm, int t, cpx wt,
-                                         const LineTw<NY / 2> &tw)
+template <int NY, bool DIST, typename Bar>
+__device__ __forceinline__ void r2c_line(cpx (&v)[16], cpx *__restrict__ Xout, const RowParams &p, int pitch, cpx *sm,
+                                         int t, cpx wt, const LineTw<NY / 2> &tw, const Bar &bar)
 {
     constexpr int L = NY / 2, G = L / 16;
-    line_fft<L, 1>(v, sm, t, 0, tw);
+    line_fft<L, 1>(v, sm, t, 0, tw, bar);
     wt = launder(wt);
 #pragma unroll
     for (int q = 0; q < 16; ++q) sm[padpos(t + q * G)] = v[q];
-    __syncthreads();
+    bar.sync();
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
         const int k = t + q * G;
@@ -107,13 +148,13 @@ __device__ __forceinline__ void r2c_line(cpx (&v)[16], cpx *__restrict__ Xout, i
         const cpx D = mk(0.5f * (Zk.x - Zm.x), 0.5f * (Zk.y - Zm.y));
         const cpx wk = (q == 0) ? wt : cmul(wt, w32(q));           // exp(-2 pi i k / NY)
         const cpx O = cmul(mul_negi(D), wk);
-        Xout[k] = cadd(E, O);
-        if (k == 0) Xout[L] = mk(Zk.x - Zk.y, 0.f);
+        Xout[line_pos<DIST>(p, k)] = cadd(E, O);
+        if (k == 0) Xout[line_pos<DIST>(p, L)] = mk(Zk.x - Zk.y, 0.f);
     }
-    if (t >= 1 && t < pitch - L) Xout[L + t] = mk(0.f, 0.f);
+    for (int k = L + 1 + t; k < pitch; k += G) Xout[line_pos<DIST>(p, k)] = mk(0.f, 0.f);
 }
 
-template <int NY, int MODE>
+template <int NY, int MODE, bool DIST>
 __global__ void __launch_bounds__(RowCfg<NY>::THREADS, RowCfg<NY>::MINB)
 row_kernel(const RowParams p)
 {
@@ -130,31 +171,35 @@ row_kernel(const RowParams p)
     LineTw<L> tw;
     tw.init(p.tw, p.twn, t);
     const cpx wt = __ldg(p.tw + (size_t)t * (p.twn / NY));
+    // one barrier per line where a line is made of whole warps, else the CTA barrier
+    typedef typename RowBarSel<(G >= 32 && C::LPC > 1)>::type Bar;
+    const Bar bar = RowBarSel<(G >= 32 && C::LPC > 1)>::make(1 + lane_line, G);
 
     cpx v[16];
     if (MODE == ROW_R2C) {
         const float2 *x = reinterpret_cast<const float2 *>(p.real_in + (size_t)row * NY);
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = __ldg(x + t + q * G);
-        cpx *out = p.spec_out + (size_t)row * p.pitch;
-        if (live) r2c_line<NY>(v, out, p.pitch, sm, t, wt, tw);
-        else r2c_line<NY>(v, out, 0, sm, t, wt, tw);   // clamped duplicate row rewrites identical values
+        cpx *out = p.spec_out + line_base(row, DIST ? p.cw : p.pitch);
+        r2c_line<NY, DIST>(v, out, p, live ? p.pitch : 0, sm, t, wt, tw, bar);   // a clamped duplicate row rewrites identical values
     } else if (MODE == ROW_C2R) {
-        c2r_line<NY>(v, p.spec_in[0] + (size_t)row * p.pitch, sm, t, wt, tw);
+        c2r_line<NY, DIST>(v, p.spec_in[0] + line_base(row, DIST ? p.cw : p.pitch), p, sm, t, wt, tw, bar);
         float2 *x = reinterpret_cast<float2 *>(p.real_out + (size_t)row * NY);
         const float s = p.negate ? -p.scale : p.scale;
 #pragma unroll
         for (int q = 0; q < 16; ++q) x[t + q * G] = mk(v[q].y * s, v[q].x * s);
     } else {
-        const size_t off = (size_t)row * p.pitch;
+        const size_t off = line_base(row, DIST ? p.cw : p.pitch);
         cpx *park0 = reinterpret_cast<cpx *>(smem_raw) + (size_t)C::LPC * LinePlan<L>::PADDED + (size_t)lane_line * (2 * L);
-        // pull the three lines that are not needed first into L2 while the first transform runs
-        {
-            constexpr int LINE_BYTES = (L + 1) * (int)sizeof(cpx);
-            for (int o = t * 128; o < LINE_BYTES; o += G * 128) {
-                prefetch_l2(reinterpret_cast<const char *>(p.spec_in[0] + off) + o);
-                prefetch_l2(reinterpret_cast<const char *>(p.spec_in[3] + off) + o);
-                prefetch_l2(reinterpret_cast<const char *>(p.spec_in[1] + off) + o);
+        // pull the lines that are not needed first into L2 while the first transform runs: the two lines of
+        // a row pair share one contiguous region of 2 * pitch elements, each line's threads fetch half of it
+        if (!DIST) {
+            const int region_bytes = 2 * p.pitch * (int)sizeof(cpx);
+            const size_t pair_off = (size_t)(row >> 1) * (size_t)(2 * p.pitch);
+            for (int o = (t + (row & 1) * G) * 128; o < region_bytes; o += 2 * G * 128) {
+                prefetch_l2(reinterpret_cast<const char *>(p.spec_in[0] + pair_off) + o);
+                prefetch_l2(reinterpret_cast<const char *>(p.spec_in[3] + pair_off) + o);
+                prefetch_l2(reinterpret_cast<const char *>(p.spec_in[1] + pair_off) + o);
             }
         }
         // One code path for the four inverse transforms (keeps the kernel inside the instruction cache):
@@ -165,7 +210,7 @@ row_kernel(const RowParams p)
 #pragma unroll 1
         for (int f = 0; f < 4; ++f) {
             const int src_field = (f == 0) ? 2 : (f == 1) ? 0 : (f == 2) ? 3 : 1;
-            c2r_line<NY>(v, p.spec_in[src_field] + off, sm, t, wt, tw);
+            c2r_line<NY, DIST>(v, p.spec_in[src_field] + off, p, sm, t, wt, tw, bar);
             cpx *park = park0 + (f >> 1) * L;
             if (f & 1) {
 #pragma unroll
@@ -192,7 +237,7 @@ row_kernel(const RowParams p)
                 J[q] = mk(J[q].x + sv.x, J[q].y + sv.y);
             }
         }
-        r2c_line<NY>(J, p.spec_out + off, live ? p.pitch : 0, sm, t, wt, tw);
+        r2c_line<NY, DIST>(J, p.spec_out + off, p, live ? p.pitch : 0, sm, t, wt, tw, bar);
     }
 }
 
