@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libxfb.so")
+LIB_PATH = os.environ.get("XFB_LIB") or os.path.join(HERE, "libxfb.so")   # XFB_LIB: A/B builds of the same ABI
 
 VORT, PSI, U, V, SRC, TFIL, DEFORM, DVORTDX, DVORTDY = range(9)
 TAB_GRADX, TAB_GRADY, TAB_LAP, TAB_LAPINV, TAB_MASK = range(5)

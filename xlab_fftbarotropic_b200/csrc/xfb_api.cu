@@ -316,7 +316,7 @@ extern "C" int xfb_profile(xfb_handle h, int enable)
     CK(cudaStreamSynchronize(h->stream));
     if (!h->ev_row) h->ev_row = new std::vector<cudaEvent_t>();
     if (!h->ev_col) h->ev_col = new std::vector<cudaEvent_t>();
-    h->ev_row_used = h->ev_col_used = 0;
+    h->ev_row_used = h->ev_col_used = h->ev_a2a_used = 0;
     h->profiling = enable != 0;
     return 0;
 }

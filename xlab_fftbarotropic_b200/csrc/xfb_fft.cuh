@@ -40,6 +40,41 @@ __device__ __forceinline__ cpx launder(cpx w)
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) and their mbarrier --------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+// global -> shared, contiguous `bytes` (multiple of 16, both addresses 16-byte aligned), completion on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 #define XFB_C8 0.70710678118654752440f
 #define XFB_C16 0.92387953251128675613f
 #define XFB_S16 0.38268343236508977173f
@@ -283,10 +318,13 @@ struct NamedBar {
 // Forward FFT of one line held as v[k] = x[t + k*G].  `sm` points at this line's padded
 // shared buffer; element address = (padpos(pos) * W + c).  All threads of the CTA must call
 // this together (it uses __syncthreads()).  On return v[k] = X[t + k*G].
-template <int L, int W, typename Bar>
+// RELEASE: the shared buffer is handed to the async proxy (a TMA bulk copy) right after the transform; every
+// thread then fences its generic-proxy accesses before the last barrier.
+template <int L, int W, typename Bar, bool RELEASE = false>
 __device__ __forceinline__ void line_fft(cpx (&v)[16], cpx *sm, const int t, const int c, const LineTw<L> &tw, const Bar &bar)
 {
     typedef LinePlan<L> P;
+    constexpr int NEX = (P::REM > 1) ? P::N16 : P::N16 - 1;     // exchanges
     int ns = 1;
 #pragma unroll
     for (int p = 0; p < P::N16; ++p) {
@@ -295,6 +333,7 @@ __device__ __forceinline__ void line_fft(cpx (&v)[16], cpx *sm, const int t, con
             exchange_write<W>(v, sm, t, c, ns);
             bar.sync();
             exchange_read<P::G, W>(v, sm, t, c);
+            if (RELEASE && p == NEX - 1) fence_proxy_async();
             bar.sync();
         }
         ns *= 16;

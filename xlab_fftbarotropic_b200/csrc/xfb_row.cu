@@ -1,5 +1,8 @@
 // xfb_row.cu -- instantiations and launcher of the K-ROW kernels.
 #include "xfb_internal.h"
+#include "xfb_rowpair.cuh"
+
+#include <cstdlib>
 
 namespace xfb {
 
@@ -27,10 +30,57 @@ static int launch_row_t(const RowParams &p, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
+// NY <= 8192: both rows of a pair as one complex line (xfb_rowpair.cuh)
+template <int NY, int MODE, bool DIST>
+static int launch_pair_t(const RowParams &p, cudaStream_t st)
+{
+    typedef PairCfg<NY> C;
+    constexpr int smem = (MODE == ROW_JAC) ? C::SMEM_JAC : C::SMEM;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(rowpair_kernel<NY, MODE, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const int npairs = p.nrows / 2;
+    int blocks = (npairs + C::PPC - 1) / C::PPC;
+    if (MODE == ROW_JAC && !DIST) {
+        // persistent: as many CTAs as are resident at once, each walks over pair groups
+        static int resident = 0;
+        if (resident == 0) {
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rowpair_kernel<NY, MODE, DIST>, C::THREADS, smem);
+            resident = sms * (per_sm > 0 ? per_sm : 1);
+        }
+        if (blocks > resident) blocks = resident;
+    }
+    rowpair_kernel<NY, MODE, DIST><<<blocks, C::THREADS, smem, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+// XFB_ROW_SINGLE=1 forces the one-row-per-line kernel (tuning / A-B knob); 16384 always uses it
+static bool use_pair_kernel(int ny)
+{
+    static const bool forced_single = getenv("XFB_ROW_SINGLE") && atoi(getenv("XFB_ROW_SINGLE")) != 0;
+    return ny <= 8192 && !forced_single;
+}
+
 template <int NY>
 static int launch_row_n(int mode, const RowParams &p, cudaStream_t st)
 {
     const bool dist = p.cw > 0;
+    if constexpr (NY <= 8192) {
+        if (use_pair_kernel(NY)) {
+            switch (mode) {
+            case ROW_R2C: return dist ? launch_pair_t<NY, ROW_R2C, true>(p, st) : launch_pair_t<NY, ROW_R2C, false>(p, st);
+            case ROW_C2R: return dist ? launch_pair_t<NY, ROW_C2R, true>(p, st) : launch_pair_t<NY, ROW_C2R, false>(p, st);
+            case ROW_JAC: return dist ? launch_pair_t<NY, ROW_JAC, true>(p, st) : launch_pair_t<NY, ROW_JAC, false>(p, st);
+            }
+            return (int)cudaErrorInvalidValue;
+        }
+    }
     switch (mode) {
     case ROW_R2C: return dist ? launch_row_t<NY, ROW_R2C, true>(p, st) : launch_row_t<NY, ROW_R2C, false>(p, st);
     case ROW_C2R: return dist ? launch_row_t<NY, ROW_C2R, true>(p, st) : launch_row_t<NY, ROW_C2R, false>(p, st);

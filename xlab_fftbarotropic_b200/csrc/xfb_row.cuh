@@ -47,7 +47,11 @@ struct RowCfg {
     static constexpr int L = NY / 2;
     static constexpr int G = L / 16;                         // threads per line
     // both lines of a row pair in one CTA wherever the shared memory allows it (NY <= 8192)
+#ifdef XFB_ROW_LPC1
+    static constexpr int THREADS = (G >= 128) ? G : 128;
+#else
     static constexpr int THREADS = (G >= 512) ? G : (2 * G >= 128) ? 2 * G : 128;
+#endif
     static constexpr int LPC = THREADS / G;                  // lines per CTA
     static constexpr int SMEM = LPC * LinePlan<L>::PADDED * (int)sizeof(cpx);
     // JAC parks -u (then -u * dvortdx) and v in shared memory between the four inverse transforms, so

@@ -1,0 +1,313 @@
+// xfb_rowpair.cuh -- K-ROW for NY <= 8192: the two rows of a pair (2m, 2m+1) are transformed TOGETHER as one
+// complex line of NY points ("two real transforms for one complex"):
+//
+//   c2r : Z[k] = A[k] + i B[k]            (k <= NY/2,  A, B the half spectra of the two rows)
+//         Z[NY-k] = conj(A[k]) + i conj(B[k])
+//         z = inverse complex DFT of Z    ->  z[n] = a[n] + i b[n]        (a, b the two real rows)
+//   r2c : z = a + i b, Z = DFT(z),  A[k] = (Z[k] + conj Z[NY-k]) / 2,  B[k] = (Z[k] - conj Z[NY-k]) / (2i)
+//
+// In the pair layout (xfb_row.cuh) A[k] and B[k] are adjacent, so every global access of this kernel is a
+// fully used 16-byte vector; there is no split/merge twiddle step at all.  Same reference loops as
+// xfb_row.cuh: main.cpp:126-135,154,168,200-201,214,225-227,237 and fftwf_backward_normalize (:37-41).
+// The imaginary parts of the DC and Nyquist bins are ignored like FFTW's c2r does.
+#pragma once
+#include "xfb_row.cuh"
+
+namespace xfb {
+
+template <int NY>
+struct PairCfg {
+    static constexpr int G = NY / 16;                          // threads per row pair
+    static constexpr int THREADS = (G >= 128) ? G : 128;
+    static constexpr int PPC = THREADS / G;                    // row pairs per CTA
+    static constexpr int SMEM = PPC * LinePlan<NY>::PADDED * (int)sizeof(cpx);
+    // JAC parks -u (then -u * dvortdx) and v (then v * dvortdy) of both rows between the transforms
+    static constexpr int SMEM_JAC = SMEM + 2 * PPC * NY * (int)sizeof(cpx);
+    static constexpr int MINB = (THREADS >= 512) ? 1 : (THREADS >= 256) ? 2 : 4;
+};
+
+// half spectra of a row pair -> on return v[q] = (b[n], a[n]) unscaled (swapped), n = t + q*G
+template <int NY, bool DIST, typename Bar>
+__device__ __forceinline__ void c2r_pair(cpx (&v)[16], const cpx *PB, const RowParams &p, cpx *sm, const int t,
+                                         const LineTw<NY> &tw, const Bar &bar)
+{
+    constexpr int G = NY / 16;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float4 ld[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int n = t + (8 * h + e) * G;
+            const int m = (h == 0) ? n : NY - n;               // h = 1: n >= NY/2, mirrored bin 1 .. NY/2
+            ld[e] = *reinterpret_cast<const float4 *>(PB + line_pos<DIST>(p, m));
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float4 x = ld[e];                                  // (A.re, A.im, B.re, B.im)
+            const int n = t + (8 * h + e) * G;
+            if ((h == 0 && e == 0 && n == 0) || (h == 1 && e == 0 && n == NY / 2)) { x.y = 0.f; x.w = 0.f; }
+            // swapped for the inverse transform: v = (Im Z, Re Z)
+            v[8 * h + e] = (h == 0) ? mk(x.y + x.z, x.x - x.w) : mk(x.z - x.y, x.x + x.w);
+        }
+    }
+    line_fft<NY, 1>(v, sm, t, 0, tw, bar);
+}
+
+// Same transform, the pair region (2 * pitch complex values, dense) already staged in this pair's FFT buffer by a
+// TMA bulk copy.  The buffer is read (two conflict-free LDS.128 streams), then reused for the exchanges; with RELEASE
+// it is handed back to the async proxy after the last exchange so the next field can be fetched during the tail.
+template <int NY, typename Bar, bool RELEASE>
+__device__ __forceinline__ void c2r_pair_staged(cpx (&v)[16], cpx *sm, const int t, const LineTw<NY> &tw, const Bar &bar)
+{
+    constexpr int G = NY / 16;
+    const float4 *st = reinterpret_cast<const float4 *>(sm);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int n = t + (8 * h + e) * G;
+            const int m = (h == 0) ? n : NY - n;
+            float4 x = st[m];
+            if ((h == 0 && e == 0 && n == 0) || (h == 1 && e == 0 && n == NY / 2)) { x.y = 0.f; x.w = 0.f; }
+            v[8 * h + e] = (h == 0) ? mk(x.y + x.z, x.x - x.w) : mk(x.z - x.y, x.x + x.w);
+        }
+    }
+    bar.sync();                                       // everyone has read the staged spectrum
+    line_fft<NY, 1, Bar, RELEASE>(v, sm, t, 0, tw, bar);
+}
+
+// v[q] = (a[n], b[n]) -> half spectra of both rows written to the pair at PBout (+ zeroed pad columns)
+template <int NY, bool DIST, typename Bar, bool RELEASE = false>
+__device__ __forceinline__ void r2c_pair(cpx (&v)[16], cpx *__restrict__ PBout, const RowParams &p, const int pitch, cpx *sm,
+                                         const int t, const LineTw<NY> &tw, const Bar &bar)
+{
+    constexpr int G = NY / 16;
+    line_fft<NY, 1>(v, sm, t, 0, tw, bar);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) sm[padpos(t + q * G)] = v[q];
+    bar.sync();
+    cpx M8[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) M8[q] = sm[padpos((NY - (t + q * G)) & (NY - 1))];      // Z[NY - n]
+    if (RELEASE) {                                              // the buffer goes back to the async proxy
+        fence_proxy_async();
+        bar.sync();
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int n = t + q * G;
+        const cpx Z = v[q];
+        const cpx M = M8[q];
+        float4 o;
+        o.x = 0.5f * (Z.x + M.x);                               // A = (Z + conj M) / 2
+        o.y = 0.5f * (Z.y - M.y);
+        o.z = 0.5f * (Z.y + M.y);                               // B = (Z - conj M) / (2i)
+        o.w = 0.5f * (M.x - Z.x);
+        *reinterpret_cast<float4 *>(PBout + line_pos<DIST>(p, n)) = o;
+    }
+    if (t == 0)                                                 // Nyquist bin: Z[NY/2] is its own mirror
+        *reinterpret_cast<float4 *>(PBout + line_pos<DIST>(p, NY / 2)) = make_float4(v[8].x, 0.f, v[8].y, 0.f);
+    for (int k = NY / 2 + 1 + t; k < pitch; k += G)
+        *reinterpret_cast<float4 *>(PBout + line_pos<DIST>(p, k)) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// forward transform in two halves so a bulk fetch can be issued between the transform and the stores:
+// begin: Z = DFT(a + i b), on return v[q] = Z[n] for q < 8 and M[q] = Z[NY - n] packed into v[8 + q]; the shared
+// buffer has been released to the async proxy.
+template <int NY, typename Bar>
+__device__ __forceinline__ void r2c_pair_begin(cpx (&v)[16], cpx *sm, const int t, const LineTw<NY> &tw, const Bar &bar)
+{
+    constexpr int G = NY / 16;
+    line_fft<NY, 1>(v, sm, t, 0, tw, bar);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) sm[padpos(t + q * G)] = v[q];
+    bar.sync();
+    const cpx nyq = v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[8 + q] = sm[padpos((NY - (t + q * G)) & (NY - 1))];
+    if (t == 0) v[8] = nyq;                                     // thread 0: Z[NY - 0] = Z[0] is not needed, keep Z[NY/2] there
+    fence_proxy_async();
+    bar.sync();
+}
+
+template <int NY, bool DIST>
+__device__ __forceinline__ void r2c_pair_finish(const cpx (&v)[16], cpx *__restrict__ PBout, const RowParams &p, const int pitch,
+                                                const int t)
+{
+    constexpr int G = NY / 16;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int n = t + q * G;
+        const cpx Z = v[q];
+        const cpx M = (q == 0 && t == 0) ? v[0] : v[8 + q];      // bin 0 mirrors itself
+        float4 o;
+        o.x = 0.5f * (Z.x + M.x);
+        o.y = 0.5f * (Z.y - M.y);
+        o.z = 0.5f * (Z.y + M.y);
+        o.w = 0.5f * (M.x - Z.x);
+        *reinterpret_cast<float4 *>(PBout + line_pos<DIST>(p, n)) = o;
+    }
+    if (t == 0) *reinterpret_cast<float4 *>(PBout + line_pos<DIST>(p, NY / 2)) = make_float4(v[8].x, 0.f, v[8].y, 0.f);
+    for (int k = NY / 2 + 1 + t; k < pitch; k += G)
+        *reinterpret_cast<float4 *>(PBout + line_pos<DIST>(p, k)) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// JAC with plain vector loads (slab runs: a line is cut into panels, not one contiguous region)
+template <int NY, bool DIST, typename Bar>
+__device__ __forceinline__ void jac_pair_direct(const RowParams &p, unsigned char *smem_raw, cpx *sm, const int lane_pair, const int t,
+                                                const size_t off, const size_t roff, const bool live, const LineTw<NY> &tw,
+                                                const Bar &bar)
+{
+    typedef PairCfg<NY> C;
+    constexpr int G = C::G;
+    cpx v[16];
+    cpx *park0 = reinterpret_cast<cpx *>(smem_raw) + (size_t)C::PPC * LinePlan<NY>::PADDED + (size_t)lane_pair * (2 * NY);
+#pragma unroll 1
+    for (int f = 0; f < 4; ++f) {
+        const int src_field = (f == 0) ? 2 : (f == 1) ? 0 : (f == 2) ? 3 : 1;
+        c2r_pair<NY, DIST>(v, p.spec_in[src_field] + off, p, sm, t, tw, bar);
+        cpx *park = park0 + (f >> 1) * NY;
+        if (f & 1) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const cpx a = park[q * G + t];
+                park[q * G + t] = mk(a.x * (v[q].y * p.scale), a.y * (v[q].x * p.scale));
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) park[q * G + t] = mk(v[q].y * p.scale, v[q].x * p.scale);
+        }
+    }
+    cpx J[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const cpx j1 = park0[q * G + t], j2 = park0[NY + q * G + t];
+        J[q] = mk(j1.x - j2.x, j1.y - j2.y);
+    }
+    if (p.real_in != nullptr) {
+        const float *sa = p.real_in + roff, *sb = sa + NY;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) J[q] = mk(J[q].x + __ldg(sa + t + q * G), J[q].y + __ldg(sb + t + q * G));
+    }
+    r2c_pair<NY, DIST>(J, p.spec_out + off, p, live ? p.pitch : 0, sm, t, tw, bar);
+}
+
+template <int NY, int MODE, bool DIST>
+__global__ void __launch_bounds__(PairCfg<NY>::THREADS, PairCfg<NY>::MINB)
+rowpair_kernel(const RowParams p)
+{
+    typedef PairCfg<NY> C;
+    constexpr int G = C::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane_pair = threadIdx.x / G;
+    const int t = threadIdx.x % G;
+    cpx *sm = reinterpret_cast<cpx *>(smem_raw) + (size_t)lane_pair * LinePlan<NY>::PADDED;
+    const int npairs = p.nrows >> 1;
+    int pair = blockIdx.x * C::PPC + lane_pair;
+    const bool live = pair < npairs;
+    if (!live) pair = npairs - 1;
+    const int rowpitch = DIST ? p.cw : p.pitch;
+    const size_t off = (size_t)pair * (size_t)(2 * rowpitch);       // pair base in a pair-layout array
+    const size_t roff = (size_t)pair * (size_t)(2 * NY);            // first of the two physical rows
+
+    LineTw<NY> tw;
+    tw.init(p.tw, p.twn, t);
+    typedef typename RowBarSel<(G >= 32 && C::PPC > 1)>::type Bar;
+    const Bar bar = RowBarSel<(G >= 32 && C::PPC > 1)>::make(1 + lane_pair, G);
+
+    cpx v[16];
+    if (MODE == ROW_R2C) {
+        const float *a = p.real_in + roff, *b = a + NY;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = mk(__ldg(a + t + q * G), __ldg(b + t + q * G));
+        r2c_pair<NY, DIST>(v, p.spec_out + off, p, live ? p.pitch : 0, sm, t, tw, bar);
+    } else if (MODE == ROW_C2R) {
+        c2r_pair<NY, DIST>(v, p.spec_in[0] + off, p, sm, t, tw, bar);
+        float *a = p.real_out + roff, *b = a + NY;
+        const float s = p.negate ? -p.scale : p.scale;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            a[t + q * G] = v[q].y * s;
+            b[t + q * G] = v[q].x * s;
+        }
+    } else if (DIST) {
+        jac_pair_direct<NY, DIST>(p, smem_raw, sm, lane_pair, t, off, roff, live, tw, bar);
+    } else {
+        // ---- persistent, TMA-staged: CTA g handles pair groups g, g + gridDim.x, ...  Every spectral line pair is
+        // fetched by ONE cp.async.bulk into the FFT buffer (free at that moment) and the fetch of the next field is
+        // issued as soon as the current transform has finished with the buffer, so it overlaps the last butterfly
+        // pass and the Jacobian arithmetic; the first field of the NEXT pair is fetched under the output stores.
+        __shared__ unsigned long long mbar_all[C::PPC];
+        unsigned long long *mbar = &mbar_all[lane_pair];
+        if (t == 0) {
+            mbar_init(mbar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        const unsigned bytes = (unsigned)(2 * p.pitch * sizeof(cpx));
+        const int ngroups = (npairs + C::PPC - 1) / C::PPC;
+        unsigned phase = 0;
+        cpx *park0 = reinterpret_cast<cpx *>(smem_raw) + (size_t)C::PPC * LinePlan<NY>::PADDED + (size_t)lane_pair * (2 * NY);
+        const cpx *const f_tu = p.spec_in[2], *const f_zx = p.spec_in[0], *const f_tv = p.spec_in[3], *const f_zy = p.spec_in[1];
+        const size_t pair_stride = (size_t)(2 * p.pitch);
+#define XFB_PAIR_OF(g_) (((g_) * C::PPC + lane_pair < npairs) ? ((g_) * C::PPC + lane_pair) : (npairs - 1))
+#define XFB_FETCH(base_, pr_)                                                   \
+    do {                                                                        \
+        if (t == 0) {                                                           \
+            mbar_expect_tx(mbar, bytes);                                        \
+            bulk_g2s(sm, (base_) + (size_t)(pr_) * pair_stride, bytes, mbar);   \
+        }                                                                       \
+    } while (0)
+        int g = blockIdx.x;
+        if (g < ngroups) XFB_FETCH(f_tu, XFB_PAIR_OF(g));
+        for (; g < ngroups; g += gridDim.x) {
+            const int pr = XFB_PAIR_OF(g);
+            const bool alive = g * C::PPC + lane_pair < npairs;
+            const size_t po = (size_t)pr * (size_t)(2 * p.pitch), ro = (size_t)pr * (size_t)(2 * NY);
+            for (int o = t * 128; o < (int)bytes; o += G * 128) {       // the other three fields towards L2
+                prefetch_l2(reinterpret_cast<const char *>(p.spec_in[0] + po) + o);
+                prefetch_l2(reinterpret_cast<const char *>(p.spec_in[3] + po) + o);
+                prefetch_l2(reinterpret_cast<const char *>(p.spec_in[1] + po) + o);
+            }
+#pragma unroll 1
+            for (int f = 0; f < 4; ++f) {
+                mbar_wait(mbar, phase);
+                phase ^= 1;
+                c2r_pair_staged<NY, Bar, true>(v, sm, t, tw, bar);
+                if (f < 3) XFB_FETCH((f == 0) ? f_zx : (f == 1) ? f_tv : f_zy, pr);      // order T_u, T_zx, T_v, T_zy
+                cpx *park = park0 + (f >> 1) * NY;
+                if (f & 1) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const cpx a = park[q * G + t];
+                        park[q * G + t] = mk(a.x * (v[q].y * p.scale), a.y * (v[q].x * p.scale));
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) park[q * G + t] = mk(v[q].y * p.scale, v[q].x * p.scale);
+                }
+            }
+            cpx J[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const cpx j1 = park0[q * G + t], j2 = park0[NY + q * G + t];
+                J[q] = mk(j1.x - j2.x, j1.y - j2.y);
+            }
+            if (p.real_in != nullptr) {
+                const float *sa = p.real_in + ro, *sb = sa + NY;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) J[q] = mk(J[q].x + __ldg(sa + t + q * G), J[q].y + __ldg(sb + t + q * G));
+            }
+            // forward transform; the buffer is released before the output stores so the next pair's first field
+            // is already on its way while they drain
+            r2c_pair_begin<NY, Bar>(J, sm, t, tw, bar);
+            const int gn = g + gridDim.x;
+            if (gn < ngroups) XFB_FETCH(f_tu, XFB_PAIR_OF(gn));
+            r2c_pair_finish<NY, DIST>(J, p.spec_out + po, p, alive ? p.pitch : 0, t);
+        }
+#undef XFB_FETCH
+#undef XFB_PAIR_OF
+    }
+}
+
+}  // namespace xfb
