@@ -1,5 +1,6 @@
 // xfb_col.cu -- instantiations and launcher of the K-COL kernels.
 #include "xfb_internal.h"
+#include "xfb_colt.cuh"
 
 namespace xfb {
 
@@ -11,19 +12,85 @@ static int env_int(const char *name, int dflt)
     return e ? atoi(e) : dflt;
 }
 
-// Column tile width W (adjacent complex columns per CTA).  A tile of NX x W complex values must fit
-// in shared memory: NX x 4 at 8192 would need 278 KB.  XFB_COL_W overrides the default where two
-// instantiations exist (tuning knob).
+// Tile width of the K-COL-private state arrays (z0 / zk / acc are tile-major, one column group per block) = the
+// number of columns the stepper transforms together: ColTCfg<NX>::FW (1 at 8192: a staged two-column tile is
+// transformed one column at a time); 16384 runs the first-generation kernel with one column per CTA.
 int col_tile_width(int nx)
 {
-    static const int forced = env_int("XFB_COL_W", 0);
     switch (nx) {
     case 256: case 512: case 1024: case 2048: return 4;
-    case 4096: return (forced == 2 || forced == 4) ? forced : 2;
-    case 8192: return (forced == 1 || forced == 2) ? forced : 2;
+    case 4096: return 2;
+    case 8192: return 1;
     case 16384: return 1;
     default: return 0;
     }
+}
+
+// ---- tensor maps for the TMA tiles of colt_kernel ------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)f;
+    }
+    return fn;
+}
+
+// pair-layout array of `rows` rows x `pitch` complex columns as a 2-D tensor of 8-byte elements:
+// inner dimension 2*pitch (column-major within a row pair: x = 2*j + (i & 1)), outer dimension rows/2
+static int make_pair_map(CUtensorMap *m, const void *base, long long rows, int pitch, int tw, int boxr)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return (int)cudaErrorNotSupported;
+    cuuint64_t dims[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)(rows / 2)};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 2 * sizeof(cpx)};
+    cuuint32_t box[2] = {(cuuint32_t)(tw * 2), (cuuint32_t)boxr};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+template <int NX, int MODE>
+static int launch_colt_t(const ColParams &p, int batch, cudaStream_t st)
+{
+    typedef ColTCfg<NX> C;
+    static int resident = 0;
+    if (resident == 0) {
+        cudaError_t e = cudaFuncSetAttribute(colt_kernel<NX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colt_kernel<NX, MODE>, C::THREADS, C::SMEM);
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    ColTMaps maps;
+    const long long rows = (long long)NX * batch;
+    if (MODE == COL_STEP) {
+        if (int e = make_pair_map(&maps.jint, p.jint, rows, p.pitch, C::TW, C::BOXR)) return e;
+    } else {
+        maps.jint = CUtensorMap();
+    }
+    for (int f = 0; f < 4; ++f)
+        if (int e = make_pair_map(&maps.t[f], p.t_out[f], rows, p.pitch, C::TW, C::BOXR)) return e;
+    const int tiles_per_member = p.pitch / C::TW, tiles_total = tiles_per_member * batch;
+    const int blocks = tiles_total < resident ? tiles_total : resident;
+    colt_kernel<NX, MODE><<<blocks, C::THREADS, C::SMEM, st>>>(p, maps, tiles_per_member, tiles_total);
+    return (int)cudaGetLastError();
+}
+
+template <int NX>
+static int launch_colt_n(int mode, const ColParams &p, int batch, cudaStream_t st)
+{
+    return mode == COL_STEP ? launch_colt_t<NX, COL_STEP>(p, batch, st) : launch_colt_t<NX, COL_PRO>(p, batch, st);
 }
 
 template <int NX, int W, int MODE>
@@ -55,15 +122,26 @@ static int launch_col_n(int mode, const ColParams &p, int batch, cudaStream_t st
 
 int launch_col(int nx, int mode, const ColParams &p, int batch, cudaStream_t st)
 {
+    // the stepper's modes run on the TMA-staged persistent kernel (XFB_COL_GEN1=1: first-generation kernel, A/B knob)
+    static const bool gen1 = env_int("XFB_COL_GEN1", 0) != 0;
+    if ((mode == COL_STEP || mode == COL_PRO) && !gen1) {
+        switch (nx) {
+        case 256: return launch_colt_n<256>(mode, p, batch, st);
+        case 512: return launch_colt_n<512>(mode, p, batch, st);
+        case 1024: return launch_colt_n<1024>(mode, p, batch, st);
+        case 2048: return launch_colt_n<2048>(mode, p, batch, st);
+        case 4096: return launch_colt_n<4096>(mode, p, batch, st);
+        case 8192: return launch_colt_n<8192>(mode, p, batch, st);
+        default: break;
+        }
+    }
     switch (nx) {
     case 256: return launch_col_n<256, 4>(mode, p, batch, st);
     case 512: return launch_col_n<512, 4>(mode, p, batch, st);
     case 1024: return launch_col_n<1024, 4>(mode, p, batch, st);
     case 2048: return launch_col_n<2048, 4>(mode, p, batch, st);
-    case 4096:
-        return col_tile_width(4096) == 2 ? launch_col_n<4096, 2>(mode, p, batch, st) : launch_col_n<4096, 4>(mode, p, batch, st);
-    case 8192:
-        return col_tile_width(8192) == 1 ? launch_col_n<8192, 1>(mode, p, batch, st) : launch_col_n<8192, 2>(mode, p, batch, st);
+    case 4096: return launch_col_n<4096, 2>(mode, p, batch, st);
+    case 8192: return launch_col_n<8192, 1>(mode, p, batch, st);
     case 16384: return launch_col_n<16384, 1>(mode, p, batch, st);
     }
     return (int)cudaErrorInvalidValue;

@@ -1,0 +1,240 @@
+// xfb_colt.cuh -- K-COL of the stepper, second generation: persistent CTAs, every strided (transposed) access
+// done by the TMA engine.
+//
+// Same fusion as col_kernel<COL_STEP / COL_PRO> (xfb_col.cuh; reference loops main.cpp:148,237,240-243,
+// 246-251,286-312 and fftwfop.cpp:87-124), different data movement:
+//   * a tile is TW adjacent spectral columns x all NX rows.  In the pair layout of the exchange arrays a tile
+//     row pair is one contiguous piece of TW*2 complex values (32 bytes for TW = 2: whole sectors), so a
+//     tile is a 2-D TMA box {TW*2, NX/2}: cp.async.bulk.tensor.2d loads the y-transformed tendency into the
+//     dense staging buffer S and stores the four x-inverse-transformed products from S.  No LDG/STG
+//     instruction touches a strided array, the loads of the NEXT tile run under the current tile's tail
+//     and the stores of field f run under the transform of field f+1.
+//   * the transforms work on FW <= TW columns at a time in a separate Stockham buffer F.  At NX = 8192 a
+//     two-column tile is transformed one column after the other (FW = 1): one butterfly per thread per pass
+//     (no register spills), at the access granularity of two columns.
+//   * CTAs are persistent (one per SM) and walk over tiles.
+// State arrays z0 / zk / acc are tile-major with tile width FW (one column group = one contiguous block).
+#pragma once
+#include <cuda.h>
+
+#include "xfb_col.cuh"
+
+namespace xfb {
+
+template <int NX>
+struct ColTCfg {
+    // staged tile width / columns transformed together
+    static constexpr int TW = (NX >= 4096) ? 2 : 4;
+    static constexpr int FW = (NX >= 8192) ? 1 : TW;
+    static constexpr int G = NX / 16;
+    static constexpr int THREADS = G * FW;
+    static constexpr int NG = TW / FW;                                   // column groups per tile
+    static constexpr int BOXR = (NX / 2 >= 256) ? 256 : NX / 2;          // row pairs per TMA box
+    static constexpr int NBOX = (NX / 2) / BOXR;
+    static constexpr int S_BYTES = NX * TW * (int)sizeof(cpx);
+    static constexpr int F_BYTES = LinePlan<NX>::PADDED * FW * (int)sizeof(cpx);
+    static constexpr int SMEM = S_BYTES + F_BYTES + 1024;                // + alignment slack
+    static constexpr int MINB = (THREADS >= 512) ? 1 : (THREADS >= 256) ? 2 : 4;
+    static_assert(THREADS >= 32 && THREADS <= 512, "bad column-group size");
+};
+
+struct ColTMaps {
+    CUtensorMap jint;
+    CUtensorMap t[4];
+};
+
+template <int NX, int MODE>
+__global__ void __launch_bounds__(ColTCfg<NX>::THREADS, ColTCfg<NX>::MINB)
+colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int tiles_per_member, const int tiles_total)
+{
+    typedef ColTCfg<NX> C;
+    constexpr int G = C::G, TW = C::TW, FW = C::FW, NG = C::NG;
+    constexpr bool KEEP = (NG == 1);
+    extern __shared__ unsigned char smem_dyn[];
+    // TMA needs 128-byte aligned shared addresses
+    unsigned char *smem_raw = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
+    cpx *S = reinterpret_cast<cpx *>(smem_raw);
+    cpx *F = reinterpret_cast<cpx *>(smem_raw + C::S_BYTES);
+    __shared__ unsigned long long full;
+
+    const int tid = threadIdx.x;
+    int t[1], c[1];
+    c[0] = tid % FW;
+    t[0] = tid / FW;
+    LineTw<NX> tw[1];
+    tw[0].init(p.tw, p.twn, t[0]);
+    if (tid == 0) {
+        mbar_init(&full, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    unsigned phase = 0;
+    const size_t srow = (size_t)p.st_row_stride;
+
+    // element (row i = t + k*G, tile column col) of S: ((i >> 1) * TW + col) * 2 + (i & 1); k-stride = G * TW
+    const int s_base = ((t[0] >> 1) * TW) * 2 + (t[0] & 1);
+
+    int tile = blockIdx.x;
+    if (MODE == COL_STEP && tile < tiles_total && tid == 0) {
+        const int member = tile / tiles_per_member, tl = tile - member * tiles_per_member;
+        mbar_expect_tx(&full, C::S_BYTES);
+#pragma unroll 1
+        for (int b = 0; b < C::NBOX; ++b)
+            tma_load_2d(S + (size_t)b * C::BOXR * TW * 2, &maps.jint, tl * TW * 2, member * (NX / 2) + b * C::BOXR, &full);
+    }
+
+    for (; tile < tiles_total; tile += gridDim.x) {
+        const int member = tile / tiles_per_member, tl = tile - member * tiles_per_member;
+        const int j0 = tl * TW;
+        const size_t moff = (size_t)member * (size_t)p.member_stride;
+        const int tmy = member * (NX / 2), tmx = tl * TW * 2;      // TMA coordinates of this tile
+        cpx v[1][16];
+        cpx zkeep[KEEP ? 16 : 1];
+
+        // ------------------------------------------------------------------ forward + epilogue
+        if (MODE == COL_STEP) {
+            // epilogue operands of this tile towards L2 (needed after the forward transform)
+            {
+                const size_t e = moff + (size_t)(tl * NG) * (size_t)p.st_tile_stride;
+                const int bytes = NX * TW * (int)sizeof(cpx);
+                for (int o = tid * 128; o < bytes; o += C::THREADS * 128) {
+                    prefetch_l2(reinterpret_cast<const char *>(p.z0 + e) + o);
+                    if (p.stage != 1) {
+                        prefetch_l2(reinterpret_cast<const char *>(p.zk + e) + o);
+                        prefetch_l2(reinterpret_cast<const char *>(p.acc + e) + o);
+                    }
+                }
+            }
+            mbar_wait(&full, phase);
+            phase ^= 1;
+#pragma unroll 1
+            for (int cg = 0; cg < NG; ++cg) {
+                const int col = cg * FW + c[0];
+                const cpx *src = S + s_base + 2 * col;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[0][k] = src[k * G * TW];
+                col_fft<NX, FW, 1>(v, F, t, c, tw);
+                const int j = p.j_base + j0 + col;
+                const float kyv = __ldg(p.ky + j);
+                const float ky2 = kyv * kyv;
+                const size_t soff = moff + (size_t)(tl * NG + cg) * (size_t)p.st_tile_stride;
+                const size_t e0 = soff + (size_t)t[0] * srow + c[0];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    cpx z0v[8], zkv[8], av[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) z0v[q] = p.z0[e0 + (size_t)((8 * h + q) * G) * srow];
+                    if (p.stage != 1) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            zkv[q] = p.zk[e0 + (size_t)((8 * h + q) * G) * srow];
+                            av[q] = p.acc[e0 + (size_t)((8 * h + q) * G) * srow];
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { zkv[q] = z0v[q]; av[q] = mk(0.f, 0.f); }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int k = 8 * h + q;
+                        const int i = t[0] + k * G;
+                        const size_t e = e0 + (size_t)(k * G) * srow;
+                        const cpx X = v[0][k];
+                        const float kxv = (float)signed_row<NX>(t[0], k) * p.kxscale;
+                        const float lap = -fmaf(kxv, kxv, ky2);
+                        // dvortdt_c += (vort_c * laplacian_coe) * NU                                  main.cpp:240-243
+                        const float tx = __fadd_rn(X.x, __fmul_rn(__fmul_rn(zkv[q].x, lap), p.nu));
+                        const float ty2 = __fadd_rn(X.y, __fmul_rn(__fmul_rn(zkv[q].y, lap), p.nu));
+                        // dealiasing mask (fftwfop.cpp:57-68)
+                        const int ii = (i <= NX / 2) ? i : NX - i;
+                        const float m = (ii * ii + j * j >= p.mask_kd_i) ? 0.0f : 1.0f;
+                        const float rx = __fmul_rn(tx, m), ry = __fmul_rn(ty2, m);
+                        cpx zn;
+                        if (p.stage == 4) {                                                          // main.cpp:309-312
+                            zn.x = __fadd_rn(z0v[q].x, __fdiv_rn(__fmul_rn(__fadd_rn(av[q].x, rx), p.dt), 6.0f));
+                            zn.y = __fadd_rn(z0v[q].y, __fdiv_rn(__fmul_rn(__fadd_rn(av[q].y, ry), p.dt), 6.0f));
+                            p.z0[e] = zn;
+                        } else {                                                                     // main.cpp:246-251
+                            const cpx an = (p.stage == 1) ? mk(rx, ry)
+                                                          : mk(__fadd_rn(av[q].x, __fmul_rn(2.0f, rx)),
+                                                               __fadd_rn(av[q].y, __fmul_rn(2.0f, ry)));
+                            p.acc[e] = an;
+                            zn.x = __fadd_rn(z0v[q].x, __fmul_rn(rx, p.dt_stage));
+                            zn.y = __fadd_rn(z0v[q].y, __fmul_rn(ry, p.dt_stage));
+                            p.zk[e] = zn;
+                        }
+                        if (KEEP) zkeep[k] = zn;
+                    }
+                }
+            }
+        }
+
+        // ------------------------------------------------------------------ prologue of the next stage + 4 inverse
+        const cpx *zsrc = (MODE == COL_PRO || p.stage == 4) ? p.z0 : p.zk;
+        if (KEEP && MODE == COL_PRO) {
+            const size_t e0 = moff + (size_t)tl * (size_t)p.st_tile_stride + (size_t)t[0] * srow + c[0];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) zkeep[k] = zsrc[e0 + (size_t)(k * G) * srow];
+        }
+#pragma unroll 1
+        for (int f = 0; f < 4; ++f) {
+#pragma unroll 1
+            for (int cg = 0; cg < NG; ++cg) {
+                const int col = cg * FW + c[0];
+                const int j = p.j_base + j0 + col;
+                const float ky = __ldg(p.ky + j);
+                const float ky2 = ky * ky;
+                if (!KEEP) {
+                    const size_t e0 = moff + (size_t)(tl * NG + cg) * (size_t)p.st_tile_stride + (size_t)t[0] * srow + c[0];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[0][k] = zsrc[e0 + (size_t)(k * G) * srow];
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int i = t[0] + k * G;
+                    const cpx z = KEEP ? zkeep[k] : v[0][k];
+                    const float kx = (float)signed_row<NX>(t[0], k) * p.kxscale;
+                    // f = 0: i kx Z, 1: i ky Z, 2: i ky Psi (u before negation), 3: i kx Psi (v);
+                    // Psi = Z / -(kx^2+ky^2), (0,0) entry divides by 1                 (fftwfop.cpp:43,112-117)
+                    float kk = (f == 0 || f == 3) ? kx : ky;
+                    if (f >= 2) {
+                        const float li = (i == 0 && j == 0) ? 1.0f : -fmaf(kx, kx, ky2);
+                        kk = __fdividef(kk, li);
+                    }
+                    v[0][k] = mk(z.x * kk, -z.y * kk);       // swap(i kk z)
+                }
+                // S is about to be overwritten: the bulk store of the previous field (or tile) must have read it.
+                // Thread 0 waits before the transform's first barrier, so every thread past that barrier knows.
+                if (cg == 0 && tid == 0) tma_wait_read_all();
+                col_fft<NX, FW, 1>(v, F, t, c, tw);
+                cpx *dst = S + s_base + 2 * col;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) dst[k * G * TW] = cswap(v[0][k]);
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                const CUtensorMap *mt = &maps.t[f];
+#pragma unroll 1
+                for (int b = 0; b < C::NBOX; ++b) tma_store_2d(mt, tmx, tmy + b * C::BOXR, S + (size_t)b * C::BOXR * TW * 2);
+                tma_commit();
+            }
+        }
+
+        // next tile's tendency into S as soon as the last store has read it
+        if (MODE == COL_STEP) {
+            const int nt = tile + gridDim.x;
+            if (nt < tiles_total && tid == 0) {
+                const int nm = nt / tiles_per_member, ntl = nt - nm * tiles_per_member;
+                tma_wait_read_all();
+                mbar_expect_tx(&full, C::S_BYTES);
+#pragma unroll 1
+                for (int b = 0; b < C::NBOX; ++b)
+                    tma_load_2d(S + (size_t)b * C::BOXR * TW * 2, &maps.jint, ntl * TW * 2, nm * (NX / 2) + b * C::BOXR, &full);
+            }
+        }
+    }
+    if (tid == 0) tma_wait_all();
+}
+
+}  // namespace xfb

@@ -75,6 +75,26 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  : "memory");
 }
 
+// 2-D tiled TMA (cp.async.bulk.tensor.2d, SASS UTMALDG / UTMASTG); `map` is a CUtensorMap in kernel-parameter space
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const void *map, int x, int y, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void *map, int x, int y, const void *src_smem)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y),
+                 "r"(smem_u32(src_smem))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores have finished READING shared memory (the buffer may be overwritten)
+__device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all committed bulk stores are complete (global memory written)
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 #define XFB_C8 0.70710678118654752440f
 #define XFB_C16 0.92387953251128675613f
 #define XFB_S16 0.38268343236508977173f
