@@ -33,7 +33,11 @@ struct ColTCfg {
     static constexpr int NBOX = (NX / 2) / BOXR;
     static constexpr int S_BYTES = NX * TW * (int)sizeof(cpx);
     static constexpr int F_BYTES = LinePlan<NX>::PADDED * FW * (int)sizeof(cpx);
-    static constexpr int SMEM = S_BYTES + F_BYTES + 1024;                // + alignment slack
+    // a second staging buffer for the incoming tendency tile where it fits (NX <= 4096): the next tile is then
+    // fetched during the whole current tile.  At 8192 one buffer serves both directions (an early prefetch.global.L2
+    // of the next tile's 32-byte pieces was measured slower: it drags whole 128-byte lines through DRAM).
+    static constexpr bool SPLIT_IN = (2 * S_BYTES + F_BYTES + 1024 <= 227 * 1024);
+    static constexpr int SMEM = (SPLIT_IN ? 2 : 1) * S_BYTES + F_BYTES + 1024;                // + alignment slack
     static constexpr int MINB = (THREADS >= 512) ? 1 : (THREADS >= 256) ? 2 : 4;
     static_assert(THREADS >= 32 && THREADS <= 512, "bad column-group size");
 };
@@ -53,8 +57,9 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
     extern __shared__ unsigned char smem_dyn[];
     // TMA needs 128-byte aligned shared addresses
     unsigned char *smem_raw = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
-    cpx *S = reinterpret_cast<cpx *>(smem_raw);
+    cpx *S = reinterpret_cast<cpx *>(smem_raw);                                   // outgoing products (and incoming tile if !SPLIT_IN)
     cpx *F = reinterpret_cast<cpx *>(smem_raw + C::S_BYTES);
+    cpx *SI = C::SPLIT_IN ? reinterpret_cast<cpx *>(smem_raw + C::S_BYTES + C::F_BYTES) : S;   // incoming tendency tile
     __shared__ unsigned long long full;
 
     const int tid = threadIdx.x;
@@ -80,7 +85,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
         mbar_expect_tx(&full, C::S_BYTES);
 #pragma unroll 1
         for (int b = 0; b < C::NBOX; ++b)
-            tma_load_2d(S + (size_t)b * C::BOXR * TW * 2, &maps.jint, tl * TW * 2, member * (NX / 2) + b * C::BOXR, &full);
+            tma_load_2d(SI + (size_t)b * C::BOXR * TW * 2, &maps.jint, tl * TW * 2, member * (NX / 2) + b * C::BOXR, &full);
     }
 
     for (; tile < tiles_total; tile += gridDim.x) {
@@ -110,7 +115,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
 #pragma unroll 1
             for (int cg = 0; cg < NG; ++cg) {
                 const int col = cg * FW + c[0];
-                const cpx *src = S + s_base + 2 * col;
+                const cpx *src = SI + s_base + 2 * col;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) v[0][k] = src[k * G * TW];
                 col_fft<NX, FW, 1>(v, F, t, c, tw);
@@ -169,6 +174,18 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
             }
         }
 
+        if (MODE == COL_STEP && C::SPLIT_IN) {
+            // every thread has read SI (it is behind the forward transform's barriers): fetch the next tile now
+            const int nt = tile + gridDim.x;
+            if (nt < tiles_total && tid == 0) {
+                const int nm = nt / tiles_per_member, ntl = nt - nm * tiles_per_member;
+                mbar_expect_tx(&full, C::S_BYTES);
+#pragma unroll 1
+                for (int b = 0; b < C::NBOX; ++b)
+                    tma_load_2d(SI + (size_t)b * C::BOXR * TW * 2, &maps.jint, ntl * TW * 2, nm * (NX / 2) + b * C::BOXR, &full);
+            }
+        }
+
         // ------------------------------------------------------------------ prologue of the next stage + 4 inverse
         const cpx *zsrc = (MODE == COL_PRO || p.stage == 4) ? p.z0 : p.zk;
         if (KEEP && MODE == COL_PRO) {
@@ -221,8 +238,8 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
             }
         }
 
-        // next tile's tendency into S as soon as the last store has read it
-        if (MODE == COL_STEP) {
+        // single staging buffer: next tile's tendency into S as soon as the last store has read it
+        if (MODE == COL_STEP && !C::SPLIT_IN) {
             const int nt = tile + gridDim.x;
             if (nt < tiles_total && tid == 0) {
                 const int nm = nt / tiles_per_member, ntl = nt - nm * tiles_per_member;
