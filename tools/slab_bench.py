@@ -112,6 +112,7 @@ def main():
     else:
         mine.copy_(chunks[0])
     sb = xfb.SlabBackend(n, rank, world, new_id(), nchunks=args.chunks, device=local_rank)
+    transport = sb.transport
     sb.set_vorticity(int(mine.data_ptr()))
     sb.step(args.warmup, dt)
     sb.sync()
@@ -120,9 +121,12 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = sb.launch_count
+    import time
     with torch.cuda.stream(stream):
         e0.record(stream)
+        h0 = time.perf_counter()
         sb.step(args.steps, dt)
+        host_enqueue_ms = (time.perf_counter() - h0) * 1e3
         e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -146,7 +150,7 @@ def main():
         result.update({
             "metric": "rk4_grid_point_steps_per_s", "value": value, "unit": "grid-pt*steps/s", "grid": n, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "scaling": "strong", "field": args.field, "dt": dt,
-            "state_finite": finite, "gpu_launches_per_rank": int(launches),
+            "state_finite": finite, "gpu_launches_per_rank": int(launches), "transport": transport, "host_enqueue_ms_per_step": host_enqueue_ms / args.steps,
             "hbm_roofline_frac": 240.0 * value / world / 1e9 / 6455.9,
             "a2a": {"ms_per_step_on_comm_stream": a2a_ms / args.steps, "exchanges": a2a["exchanges"],
                     "nvlink_bytes_per_gpu_per_step": nv_bytes,

@@ -21,7 +21,7 @@ SYMBOLS = [
     "xfb_invert_laplacian", "xfb_dealias", "xfb_get_table", "xfb_r2c", "xfb_c2r", "xfb_set_vorticity",
     "xfb_set_spectrum", "xfb_get_spectrum", "xfb_set_source", "xfb_step", "xfb_get_field", "xfb_get_keff_hist",
     "xfb_invert_pres", "xfb_launch_count", "xfb_stream", "xfb_size_supported", "xfb_profile", "xfb_profile_read",
-    "xfb_slab_partition", "xfb_nccl_unique_id", "xfb_create_dist", "xfb_profile_read_a2a",
+    "xfb_slab_partition", "xfb_nccl_unique_id", "xfb_create_dist", "xfb_profile_read_a2a", "xfb_slab_transport",
     "xfb_loopback_create", "xfb_loopback_destroy", "xfb_loopback_set_vorticity", "xfb_loopback_set_source",
     "xfb_loopback_step", "xfb_loopback_get_field", "xfb_loopback_launch_count",
 ]
@@ -70,6 +70,7 @@ def load():
     L.xfb_nccl_unique_id.argtypes = [C.c_char_p]
     L.xfb_create_dist.argtypes = [C.POINTER(vp), ci, ci, cf, cf, cf, ci, ci, ci, ci, C.c_char_p]
     L.xfb_profile_read_a2a.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    L.xfb_slab_transport.argtypes = [vp]
     L.xfb_loopback_create.argtypes = [C.POINTER(vp), ci, ci, cf, cf, cf, ci, ci, ci]
     L.xfb_loopback_destroy.argtypes = [vp]
     L.xfb_loopback_set_vorticity.argtypes = [vp, vp]
@@ -260,6 +261,10 @@ class SlabBackend(Backend):
             out = np.empty((self.rows, self.ny), np.float32)
         self._ck(self._L.xfb_get_field(self._h, 0, which, _ptr(out)))
         return out
+
+    @property
+    def transport(self):
+        return {0: "none", 1: "nccl send/recv", 2: "p2p copy engines (CUDA IPC)"}[int(self._L.xfb_slab_transport(self._h))]
 
     def a2a_read(self):
         ms, n = C.c_double(), C.c_longlong()

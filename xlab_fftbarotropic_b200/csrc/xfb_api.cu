@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -233,11 +234,15 @@ int xfb::create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float 
         h->mask_kd = (double)(float)((double)dkx * dkx + (double)dky * dky);
     }
     const size_t sb = sizeof(cpx) * h->hpad * batch;
-    cpx **state[] = {&h->z0, &h->zk, &h->acc, &h->jint, &h->t[0], &h->t[1], &h->t[2], &h->t[3]};
+    cpx **state[] = {&h->z0, &h->zk, &h->acc, &h->jint};
     for (auto pp : state) {
         if (dev_alloc((void **)pp, sb)) return XFB_E_CUDA;
         CK(cudaMemsetAsync(*pp, 0, sb, h->stream));
     }
+    // the four product arrays back to back (one 2-D copy moves a block of all four in the slab exchange)
+    if (dev_alloc((void **)&h->t_block, 4 * sb)) return XFB_E_CUDA;
+    CK(cudaMemsetAsync(h->t_block, 0, 4 * sb, h->stream));
+    for (int f = 0; f < 4; ++f) h->t[f] = h->t_block + (size_t)f * h->hpad * batch;
     if (dev_alloc((void **)&h->real_a, sizeof(float) * h->grids) || dev_alloc((void **)&h->real_b, sizeof(float) * h->grids) ||
         dev_alloc((void **)&h->real_c, sizeof(float) * h->grids) ||
         dev_alloc((void **)&h->spec_a, sizeof(cpx) * h->hpad) || dev_alloc((void **)&h->spec_b, sizeof(cpx) * h->hpad))
@@ -249,12 +254,20 @@ int xfb::create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float 
     CK(cudaMemsetAsync(h->spec_a, 0, sizeof(cpx) * h->hpad, h->stream));
     CK(cudaMemsetAsync(h->spec_b, 0, sizeof(cpx) * h->hpad, h->stream));
     if (nranks > 1) {
-        cpx **rb[] = {&h->jint_recv, &h->tr[0], &h->tr[1], &h->tr[2], &h->tr[3]};
-        for (auto pp : rb) {
-            if (dev_alloc((void **)pp, sb)) return XFB_E_CUDA;
-            CK(cudaMemsetAsync(*pp, 0, sb, h->stream));
-        }
+        if (dev_alloc((void **)&h->recv_block, 5 * sb)) return XFB_E_CUDA;
+        CK(cudaMemsetAsync(h->recv_block, 0, 5 * sb, h->stream));
+        h->jint_recv = h->recv_block;
+        for (int f = 0; f < 4; ++f) h->tr[f] = h->recv_block + (size_t)(1 + f) * h->hpad;
+        if (dev_alloc((void **)&h->sync_buf, sizeof(float))) return XFB_E_CUDA;
+        CK(cudaMemsetAsync(h->sync_buf, 0, sizeof(float), h->stream));
         CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        h->ncopy = 1;     // measured: several copy streams are SLOWER when the SMs keep HBM busy (tools/probes/probe_p2p_copy.cu)
+        if (const char *e = getenv("XFB_SLAB_COPY_STREAMS")) h->ncopy = atoi(e) < 1 ? 1 : (atoi(e) > 4 ? 4 : atoi(e));
+        for (int i = 0; i < 4; ++i) {
+            CK(cudaStreamCreateWithFlags(&h->copy_stream[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         for (auto &ev : h->ev_chunk) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto &ev : h->ev_comm) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
@@ -274,9 +287,8 @@ int xfb::destroy_impl(xfb_handle h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
-    void *ptrs[] = {h->tw, h->kx, h->ky, h->kx2, h->ky2, h->z0, h->zk, h->acc, h->jint, h->t[0], h->t[1], h->t[2],
-                    h->t[3], h->src, h->real_a, h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b,
-                    h->jint_recv, h->tr[0], h->tr[1], h->tr[2], h->tr[3]};
+    void *ptrs[] = {h->tw, h->kx, h->ky, h->kx2, h->ky2, h->z0, h->zk, h->acc, h->jint, h->t_block, h->src, h->real_a,
+                    h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b, h->recv_block, h->sync_buf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto pool : {h->ev_row, h->ev_col, h->ev_a2a})
@@ -287,6 +299,12 @@ int xfb::destroy_impl(xfb_handle h)
     if (h->comm_stream) {
         for (auto ev : h->ev_chunk) cudaEventDestroy(ev);
         for (auto ev : h->ev_comm) cudaEventDestroy(ev);
+        for (int i = 0; i < 4; ++i) {
+            cudaStreamSynchronize(h->copy_stream[i]);
+            cudaStreamDestroy(h->copy_stream[i]);
+            cudaEventDestroy(h->ev_copy[i]);
+        }
+        cudaEventDestroy(h->ev_fork);
         cudaStreamDestroy(h->comm_stream);
     }
     cudaStreamDestroy(h->stream);

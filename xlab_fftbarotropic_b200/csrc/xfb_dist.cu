@@ -19,6 +19,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -35,6 +36,8 @@ struct NcclApi {
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*GroupStart)();
     ncclResult_t (*GroupEnd)();
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
     const char *(*GetErrorString)(ncclResult_t);
 };
 
@@ -60,6 +63,8 @@ static int nccl_load()
     SYM(Recv, "ncclRecv");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
+    SYM(AllGather, "ncclAllGather");
+    SYM(AllReduce, "ncclAllReduce");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
     g_nccl = a;
@@ -112,6 +117,56 @@ static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *
         return 0;
     }
     const int me = h0->rank;
+    if (h0->p2p) {
+        // Copy-engine pushes straight into the peers' receive arrays (mapped over CUDA IPC): one 2-D copy per peer
+        // and piece moves the blocks of all column chunks (ROW2COL) or of all `na` arrays (COL2ROW).  The copies
+        // fork from `st` onto h->ncopy streams (several copy engines in flight) and join it again; every block is
+        // cut into `pieces` column ranges when there are fewer peers than streams.  Peers are visited in a rotated
+        // order so that at any moment every GPU is the target of one sender.  Completion on the RECEIVER is
+        // signalled by the phase barrier (phase_barrier below), not here.
+        const int ncs = h0->ncopy;
+        CK(cudaEventRecord(h0->ev_fork, st));
+        for (int s = 0; s < ncs; ++s) CK(cudaStreamWaitEvent(h0->copy_stream[s], h0->ev_fork, 0));
+        const int pieces = (T->nranks - 1 >= ncs) ? 1 : ncs / (T->nranks - 1);
+        const size_t piece_elems = ((count + pieces - 1) / pieces + 1) & ~(size_t)1;      // even: 16-byte aligned pieces
+        int slot = 0;
+        for (int i = 0; i < T->nranks; ++i) {
+            const int q = (me + i) % T->nranks;
+            cpx *peer = h0->peer_recv[q];
+            for (int pc = 0; pc < pieces; ++pc) {
+                const size_t e0 = (size_t)pc * piece_elems;
+                if (e0 >= count) break;
+                const size_t wbytes = sizeof(cpx) * ((count - e0 < piece_elems) ? count - e0 : piece_elems);
+                cudaStream_t cs = h0->copy_stream[slot++ % ncs];
+                if (dir == ROW2COL) {
+                    // array 0 of the receive block = jint_recv ; chunks c0..c1-1 are rows*cw apart here, NX*cw apart there
+                    const cpx *src = row_ptrs_of_rank[0] + row_off(h0, q, c0, r0) + e0;
+                    cpx *dst = peer + col_off(h0, me, c0, r0) + e0;
+                    CK(cudaMemcpy2DAsync(dst, sizeof(cpx) * (size_t)h0->nx * h0->pitch, src, sizeof(cpx) * (size_t)h0->rows * h0->pitch,
+                                         wbytes, (size_t)(c1 - c0), cudaMemcpyDeviceToDevice, cs));
+                } else {
+                    // arrays 1..4 of the receive block = tr[0..3] (or tr[0] alone, na == 1)
+                    for (int c = c0; c < c1; ++c) {
+                        if (na == 4) {
+                            const cpx *src = col_ptrs_of_rank[0] + col_off(h0, q, c, r0) + e0;     // t[0]; t[1..3] follow hpad apart
+                            cpx *dst = peer + h0->hpad + row_off(h0, me, c, r0) + e0;
+                            CK(cudaMemcpy2DAsync(dst, sizeof(cpx) * h0->hpad, src, sizeof(cpx) * h0->hpad, wbytes, 4,
+                                                 cudaMemcpyDeviceToDevice, cs));
+                        } else {
+                            for (int a = 0; a < na; ++a)
+                                CK(cudaMemcpyAsync(peer + (size_t)(1 + a) * h0->hpad + row_off(h0, me, c, r0) + e0,
+                                                   col_ptrs_of_rank[a] + col_off(h0, q, c, r0) + e0, wbytes, cudaMemcpyDeviceToDevice, cs));
+                        }
+                    }
+                }
+            }
+        }
+        for (int s = 0; s < ncs; ++s) {
+            CK(cudaEventRecord(h0->ev_copy[s], h0->copy_stream[s]));
+            CK(cudaStreamWaitEvent(st, h0->ev_copy[s], 0));
+        }
+        return 0;
+    }
     NCK(g_nccl.GroupStart());
     for (int a = 0; a < na; ++a)
         for (int c = c0; c < c1; ++c)
@@ -164,6 +219,18 @@ static int launch_col_chunk(xfb_handle h, int mode, int chunk, int stage, float 
     return 0;
 }
 
+// End of an exchange phase on the NCCL/P2P transports.  With copy-engine pushes nobody knows when the peers' data has
+// landed: a one-float all-reduce on the communication stream is the barrier (every rank enters it after its own
+// pushes, so leaving it means all pushes into this rank are complete -- and that every peer has finished reading
+// what the NEXT phase will overwrite).  ncclSend/ncclRecv pairs synchronise by themselves.
+static int phase_barrier(Team *T, cudaStream_t st)
+{
+    xfb_handle h0 = T->local[0];
+    if (!h0->p2p) return 0;
+    NCK(g_nccl.AllReduce(h0->sync_buf, h0->sync_buf, 1, ncclFloat, ncclSum, T->comm, st));
+    return 0;
+}
+
 // events around the exchanges when profiling (NCCL transport only; the loopback shares the compute stream)
 static void a2a_mark(xfb_handle h, cudaStream_t st)
 {
@@ -193,6 +260,7 @@ static int rows_then_exchange(Team *T, F produce, GR row_of, GC col_of)
         if (int e = exchange(T, ROW2COL, rp, cp, 1, 0, C, i * rc, (i + 1) * rc, h0->comm_stream)) return e;
         a2a_mark(h0, h0->comm_stream);
     }
+    if (int e = phase_barrier(T, h0->comm_stream)) return e;
     CK(cudaEventRecord(h0->ev_comm[0], h0->comm_stream));
     CK(cudaStreamWaitEvent(h0->stream, h0->ev_comm[0], 0));
     return 0;
@@ -222,6 +290,7 @@ static int cols_then_exchange(Team *T, F produce, GC col_of, GR row_of, int na)
         if (int e = exchange(T, COL2ROW, rp, cp, na, c, c + 1, 0, h0->rows, h0->comm_stream)) return e;
         a2a_mark(h0, h0->comm_stream);
     }
+    if (int e = phase_barrier(T, h0->comm_stream)) return e;
     CK(cudaEventRecord(h0->ev_comm[1], h0->comm_stream));
     CK(cudaStreamWaitEvent(h0->stream, h0->ev_comm[1], 0));
     return 0;
@@ -391,6 +460,8 @@ void dist_release(xfb_handle h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->comm_stream);
+    for (int q = 0; q < T->nranks; ++q)
+        if (h->p2p && q != h->rank && h->peer_recv[q]) cudaIpcCloseMemHandle(h->peer_recv[q]);
     if (T->comm) g_nccl.CommDestroy(T->comm);
     delete T;
     h->team = nullptr;
@@ -443,7 +514,45 @@ extern "C" int xfb_create_dist(xfb_handle *out, int nx, int ny, float lx, float 
     }
     h->team = T;
     h->ev_a2a = new std::vector<cudaEvent_t>();
+    // peer-to-peer transport: export the receive block, gather everybody's handle with NCCL, map the peers' blocks.
+    // XFB_SLAB_NCCL=1 keeps the grouped ncclSend/ncclRecv transport (A/B knob and fallback where IPC is not possible).
+    const char *force_nccl = getenv("XFB_SLAB_NCCL");
+    if (!(force_nccl && atoi(force_nccl) != 0)) {
+        cudaIpcMemHandle_t mine, *all_d = nullptr;
+        std::vector<cudaIpcMemHandle_t> all(nranks);
+        bool ok = cudaIpcGetMemHandle(&mine, h->recv_block) == cudaSuccess &&
+                  cudaMalloc((void **)&all_d, sizeof(mine) * nranks) == cudaSuccess;
+        if (ok) {
+            cudaMemcpyAsync(all_d + rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->comm_stream);
+            ok = g_nccl.AllGather(all_d + rank, all_d, sizeof(mine), ncclChar, T->comm, h->comm_stream) == ncclSuccess &&
+                 cudaMemcpyAsync(all.data(), all_d, sizeof(mine) * nranks, cudaMemcpyDeviceToHost, h->comm_stream) == cudaSuccess &&
+                 cudaStreamSynchronize(h->comm_stream) == cudaSuccess;
+        }
+        int mapped = ok ? 1 : 0;
+        for (int q = 0; ok && q < nranks; ++q) {
+            if (q == rank) { h->peer_recv[q] = h->recv_block; continue; }
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { mapped = 0; cudaGetLastError(); break; }
+            h->peer_recv[q] = (cpx *)ptr;
+        }
+        if (all_d) cudaFree(all_d);
+        // everybody must agree on the transport: min over ranks of `mapped`
+        float flag = (float)mapped, *flag_d = h->sync_buf;
+        cudaMemcpyAsync(flag_d, &flag, sizeof(float), cudaMemcpyHostToDevice, h->comm_stream);
+        g_nccl.AllReduce(flag_d, flag_d, 1, ncclFloat, ncclMin, T->comm, h->comm_stream);
+        cudaMemcpyAsync(&flag, flag_d, sizeof(float), cudaMemcpyDeviceToHost, h->comm_stream);
+        cudaStreamSynchronize(h->comm_stream);
+        h->p2p = flag > 0.5f;
+        cudaMemsetAsync(h->sync_buf, 0, sizeof(float), h->comm_stream);
+        cudaStreamSynchronize(h->comm_stream);
+    }
     return 0;
+}
+
+extern "C" int xfb_slab_transport(xfb_handle h)
+{
+    if (!h || h->nranks <= 1) return 0;
+    return h->p2p ? 2 : 1;       // 2: copy-engine pushes over CUDA IPC peer mappings, 1: ncclSend/ncclRecv
 }
 
 extern "C" int xfb_profile_read_a2a(xfb_handle h, double *a2a_ms, long long *exchanges)

@@ -60,8 +60,15 @@ struct xfb_handle_s {
     int rank, nranks, rows, nchunks, pitch_g, col0;
     unsigned cw_magic;
     xfb::Team *team;
-    xfb::cpx *jint_recv, *tr[4];    // receive sides of the two transposes
+    xfb::cpx *jint_recv, *tr[4];    // receive sides of the two transposes: ONE allocation (recv_block), exported over CUDA IPC
+    xfb::cpx *t_block, *recv_block; // t[0..3] back to back ; jint_recv, tr[0..3] back to back
+    xfb::cpx *peer_recv[16];        // recv_block of every rank mapped into this process (peer-to-peer over NVLink)
+    float *sync_buf;                // 1 float, reduced over all ranks as the phase barrier
+    bool p2p;                       // exchange by copy-engine pushes into peer_recv (else ncclSend/ncclRecv)
     cudaStream_t comm_stream;
+    cudaStream_t copy_stream[4];    // p2p transport: the pushes of one exchange are spread over several copy engines
+    cudaEvent_t ev_copy[4], ev_fork;
+    int ncopy;
     cudaEvent_t ev_chunk[16], ev_comm[2];
     // optional per-kernel timing (xfb_profile)
     bool profiling;
