@@ -1,6 +1,7 @@
 // xfb_col.cu -- instantiations and launcher of the K-COL kernels.
 #include "xfb_internal.h"
 #include "xfb_colt.cuh"
+#include "xfb_coltc.cuh"
 
 namespace xfb {
 
@@ -87,9 +88,45 @@ static int launch_colt_t(const ColParams &p, int batch, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
+// NX = 8192: two-CTA clusters share a two-column tile (xfb_coltc.cuh)
+template <int NX, int MODE>
+static int launch_coltc_t(const ColParams &p, int batch, cudaStream_t st)
+{
+    typedef ColTCCfg<NX> C;
+    static int blocks_max = 0;
+    if (blocks_max == 0) {
+        cudaError_t e = cudaFuncSetAttribute(coltc_kernel<NX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        blocks_max = sms & ~1;
+    }
+    ColTMaps maps;
+    const long long rows = (long long)NX * batch;
+    if (MODE == COL_STEP) {
+        if (int e = make_pair_map(&maps.jint, p.jint, rows, p.pitch, 2, C::BOXR)) return e;
+    } else {
+        maps.jint = CUtensorMap();
+    }
+    for (int f = 0; f < 4; ++f)
+        if (int e = make_pair_map(&maps.t[f], p.t_out[f], rows, p.pitch, 2, C::BOXR)) return e;
+    const int tiles_per_member = p.pitch / 2, tiles_total = tiles_per_member * batch;
+    const int blocks = 2 * tiles_total < blocks_max ? 2 * tiles_total : blocks_max;
+    coltc_kernel<NX, MODE><<<blocks, C::THREADS, C::SMEM, st>>>(p, maps, tiles_per_member, tiles_total);
+    return (int)cudaGetLastError();
+}
+
 template <int NX>
 static int launch_colt_n(int mode, const ColParams &p, int batch, cudaStream_t st)
 {
+    if constexpr (NX == 8192) {
+        // opt-in: measured SLOWER than colt_kernel<8192> (1.14 vs 0.92 ms per launch at 8192^2): the DSMEM
+        // redistribution and ten cluster barriers per tile cost more than the re-reads and the late fetch they remove
+        static const bool cluster = env_int("XFB_COL_CLUSTER", 0) != 0;
+        if (cluster)
+            return mode == COL_STEP ? launch_coltc_t<NX, COL_STEP>(p, batch, st) : launch_coltc_t<NX, COL_PRO>(p, batch, st);
+    }
     return mode == COL_STEP ? launch_colt_t<NX, COL_STEP>(p, batch, st) : launch_colt_t<NX, COL_PRO>(p, batch, st);
 }
 
