@@ -43,6 +43,16 @@ def dt_for(n: int) -> float:
     return float(np.float32(0.6 * 2.83 / (kmax * 83.0)))
 
 
+def measured_traffic(grid: int, which: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture, or None"""
+    p = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+    try:
+        d = json.load(open(p))
+        return float(d[str(grid)][which]["dram_bytes_per_launch"]), d["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -293,9 +303,13 @@ def gpu_arm(args):
     dominant = "col" if prof["col_ms"] >= prof["row_ms"] else "row"
     achieved = col_gbs if dominant == "col" else row_gbs
     step_gbs = ALGO_BYTES_PER_PT_STEP * value / world / 1e9
+    traffic, traffic_src = measured_traffic(n, "col_step" if dominant == "col" else "row_jac") if args.members == 1 else (None, None)
+    names = {"col": "colt_kernel<COL_STEP>" if n <= 8192 else "col_kernel<COL_STEP>",
+             "row": "rowpair_kernel<ROW_JAC>" if n <= 8192 else "row_kernel<ROW_JAC>"}
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "kernel": "col_kernel<COL_STEP>" if dominant == "col" else "row_kernel<ROW_JAC>",
+        "traffic": traffic, "traffic_source": traffic_src, "kernel": names[dominant],
+        "algo_bytes_per_launch": (ALGO_BYTES_COL if dominant == "col" else ALGO_BYTES_ROW) * pts,
         "peak_source": peak_src,
         "kernels": {
             "col_step": {"avg_ms": col_avg, "launches": prof["col_launches"], "algo_bytes_per_pt": ALGO_BYTES_COL,
@@ -334,21 +348,65 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
+def slab_arm(args):
+    """--slab: ONE grid slab-decomposed over the GPUs (one rank per GPU, NVLink all-to-all per 2-D transform);
+    strong scaling.  Same JSON contract; the work is tools/slab_bench.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import slab_bench
+    a = argparse.Namespace(grid=args.grid, steps=args.steps, warmup=args.warmup, chunks=args.chunks, check=args.slab_check,
+                           field="const" if args.grid >= 16384 else "elliptic", e2e_steps=max(1, min(args.e2e_steps, 3)))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    r = slab_bench.run(a)
+    clocks = sampler.stop()
+    if r is None:
+        return
+    peak, peak_src = measured_peaks()
+    world = r["n_gpus"]
+    line = {
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{r['field']} vortex {args.grid}^2 RK4 step slab-decomposed over {world} GPU(s), dt={r['dt']:g}s, "
+                               f"{args.chunks} chunks, transport {r['transport']}",
+                   "grid": args.grid, "l2": "per-rank working set is larger than the 126 MB L2", "state_finite": r["state_finite"],
+                   "check_vs_single_gpu": r.get("check")},
+        "clocks": clocks, "gpu_launches": r["gpu_launches_per_rank"] * world,
+        "e2e": {k: r["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "steps", "ms_per_step")},
+        "roofline": {"bound": "hbm", "achieved": ALGO_BYTES_PER_PT_STEP * r["value"] / world / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": ALGO_BYTES_PER_PT_STEP * r["value"] / world / 1e9 / peak, "traffic": None,
+                     "kernel": "whole step per rank (K-ROW + K-COL + exchange)", "peak_source": peak_src},
+        "nvlink": {"bytes_per_gpu_per_step": r["a2a"]["nvlink_bytes_per_gpu_per_step"],
+                   "a2a_ms_per_step_on_comm_stream": r["a2a"]["ms_per_step_on_comm_stream"],
+                   "achieved_gbs_per_direction": r["a2a"]["achieved_gbs_per_direction"], "peak_gbs": 770.0,
+                   "peak_source": "B200_PROFILING.md measured peer copy"},
+    }
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="xfb", choices=["xfb", "reference"])
-    ap.add_argument("--grid", type=int, default=8192)
+    ap.add_argument("--grid", type=int, default=None, help="default 8192 (16384 with --slab)")
     ap.add_argument("--members", type=int, default=1, help="ensemble members per GPU")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--ref-grid", type=int, default=2048, help="grid of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slab", action="store_true", help="one grid slab-decomposed over the ranks (default: one ensemble member per GPU)")
+    ap.add_argument("--chunks", type=int, default=4, help="--slab: chunks of the compute/exchange overlap")
+    ap.add_argument("--slab-check", type=int, default=0, help="--slab: first verify against the single-GPU path at this grid size")
     args = ap.parse_args()
+    if args.grid is None:
+        args.grid = 16384 if args.slab else 8192
     if args.impl == "reference":
         reference_arm(args)
+    elif args.slab:
+        slab_arm(args)
     else:
         gpu_arm(args)
 

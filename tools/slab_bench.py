@@ -31,7 +31,15 @@ def main():
     ap.add_argument("--chunks", type=int, default=4)
     ap.add_argument("--check", type=int, default=0)
     ap.add_argument("--field", default="const", choices=["const", "elliptic"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
+    res = run(args)
+    if res is not None:
+        print(json.dumps(res))
+
+
+def run(args):
+    """-> result dict on rank 0, None elsewhere (also used by `bench.py --slab`)"""
 
     import torch
     import torch.distributed as dist
@@ -141,6 +149,27 @@ def main():
         a2a_ms = 0.0
     out = sb.get_field(xfb.capi.VORT)
     finite = bool(np.isfinite(out).all())
+    # end to end through the C ABI with HOST buffers: every step uploads this rank's rows and reads them back
+    e2e_steps = max(1, getattr(args, "e2e_steps", 3))
+    host_in = mine.cpu().pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
+    hin, hout = int(host_in.data_ptr()), int(host_out.data_ptr())
+    sb.set_vorticity(host_in.numpy())
+    sb.step(1, dt)
+    barrier()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            sb._ck(sb._L.xfb_set_vorticity(sb._h, 0, hin))
+            sb.step(1, dt)
+            sb._ck(sb._L.xfb_get_field(sb._h, 0, xfb.capi.VORT, hout))
+        e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t2 = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t2[0])
     sb.close()
     if rank == 0:
         G = float(n) * n
@@ -158,10 +187,12 @@ def main():
                     "peak_gbs": 770.0, "peak_source": "B200_PROFILING.md peer copy"},
             "kernels": {"row_ms_per_step": prof["row_ms"] / args.steps, "col_ms_per_step": prof["col_ms"] / args.steps,
                         "note": "row/col spans include the wait for their exchanges"},
+            "e2e": {"value": G * e2e_steps / (ms_e2e * 1e-3), "unit": "grid-pt*steps/s", "steps": e2e_steps,
+                    "ms_per_step": ms_e2e / e2e_steps, "h2d_bytes_per_step": 4 * G, "d2h_bytes_per_step": 4 * G},
         })
-        print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+    return result if rank == 0 else None
 
 
 if __name__ == "__main__":
