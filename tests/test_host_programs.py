@@ -57,6 +57,29 @@ def test_main_out_matches_reference_binary():
 
 
 @pytest.mark.gpu
+def test_example_sh_default_grid_768():
+    """test/01-runtest/example.sh with the reference's compile-time defaults: makefield-elliptic-vortex.out writes
+    input/initial_vorticity.bin at NPTS = 768 (src/configuration.hpp:18), main.out runs it with no size flag;
+    compared file by file with the UNMODIFIED reference binary built at 768 (shortened to 6 steps, record every 3)."""
+    from oracle import oracle as orc
+    n, steps, rec = 768, 6, 3
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "input"))
+        os.makedirs(os.path.join(d, "output"))
+        subprocess.run([os.path.join(BIN, "makefield-elliptic-vortex.out")], cwd=d, check=True, stderr=subprocess.DEVNULL)
+        v0 = np.fromfile(os.path.join(d, "input", "initial_vorticity.bin"), dtype="<f4")
+        assert v0.size == n * n
+        v0 = v0.reshape(n, n)
+        ref = orc.run_reference_main(v0, n, 3.0, steps, rec)
+        r = subprocess.run([os.path.join(BIN, "main.out"), "-t", str(steps), "-r", str(rec)], cwd=d, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        for s in (0, 3):
+            for k in ("vort", "psi", "u", "v"):
+                got = np.fromfile(os.path.join(d, f"output/{k}_step_{s}.bin"), dtype="<f4").reshape(n, n)
+                assert rel_l2(got, ref[(k, s)]) < 1e-5, (k, s)
+
+
+@pytest.mark.gpu
 def test_main_out_fifo_forcing_and_invert_pres():
     from oracle import oracle as orc
     import fields

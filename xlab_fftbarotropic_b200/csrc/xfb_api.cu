@@ -56,6 +56,7 @@ bool xfb::is_device_ptr(const void *p)
 extern "C" int xfb_size_supported(int nx, int ny)
 {
     if (col_tile_width(nx) > 0 && row_size_ok(ny)) return 1;
+    if (generic_size_ok(nx, ny)) return 2;
     return 0;
 }
 
@@ -169,8 +170,11 @@ int xfb::create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float 
     *out = nullptr;
     if (batch < 1) return fail(XFB_E_ARG, "xfb_create: batch must be >= 1");
     if (nranks > 1 && batch != 1) return fail(XFB_E_ARG, "slab handles hold one member");
-    if (!xfb_size_supported(nx, ny))
-        return fail(XFB_E_SIZE, "xfb_create: grid %dx%d not supported (powers of two 256..16384)", nx, ny);
+    const int size_class = xfb_size_supported(nx, ny);
+    if (!size_class)
+        return fail(XFB_E_SIZE, "xfb_create: grid %dx%d not supported (fused kernels: powers of two 256..16384; generic path: "
+                                "even sizes 2^a 3^b 5^c up to 4096)", nx, ny);
+    if (size_class == 2 && nranks > 1) return fail(XFB_E_SIZE, "slab decomposition needs a power-of-two grid");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -196,6 +200,7 @@ int xfb::create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float 
             if ((unsigned)(((unsigned long long)k * h->cw_magic) >> 32) != k / (unsigned)h->pitch)
                 return fail(XFB_E_SIZE, "internal: magic division fails for k=%u cw=%d", k, h->pitch);
     }
+    if (size_class == 2) h->pitch = h->pitch_g = h->hy;       // generic path: reference layout, no padding
     // `pitch` is the pitch of the column-side arrays (one chunk of this rank's columns; all columns on one GPU)
     h->grids = (size_t)h->rows * ny; h->hgrids = (size_t)nx * h->hy; h->hpad = (size_t)nx * h->pitch * nchunks;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -271,6 +276,7 @@ int xfb::create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float 
         for (auto &ev : h->ev_chunk) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto &ev : h->ev_comm) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
+    if (size_class == 2 && generic_create(h)) return XFB_E_CUDA;
     CK(cudaStreamSynchronize(h->stream));
     *out = h;
     return 0;
@@ -287,6 +293,7 @@ int xfb::destroy_impl(xfb_handle h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+    generic_destroy(h);
     void *ptrs[] = {h->tw, h->kx, h->ky, h->kx2, h->ky2, h->z0, h->zk, h->acc, h->jint, h->t_block, h->src, h->real_a,
                     h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b, h->recv_block, h->sync_buf};
     for (void *p : ptrs)
@@ -456,6 +463,7 @@ void xfb::fill_col(xfb_handle h, ColParams &p, int chunk)
 // real [nx][ny] (device) -> padded spectrum (device), via `tmp` (padded)
 static int fwd2d(xfb_handle h, const float *real_in, cpx *tmp, cpx *spec_out)
 {
+    if (h->generic) return generic_fwd2d(h, real_in, tmp, spec_out);
     RowParams r; fill_row(h, r, h->nx);
     r.real_in = real_in; r.spec_out = tmp;
     CKL(h, launch_row(h->ny, ROW_R2C, r, h->stream));
@@ -468,6 +476,7 @@ static int fwd2d(xfb_handle h, const float *real_in, cpx *tmp, cpx *spec_out)
 // padded spectrum (device) -> real [nx][ny] (device), scaled by `scale`; spec_in is preserved
 static int inv2d(xfb_handle h, const cpx *spec_in, cpx *tmp, float *real_out, float scale, int negate)
 {
+    if (h->generic) return generic_inv2d(h, spec_in, tmp, real_out, scale, negate);
     ColParams c; fill_col(h, c);
     c.inv_in = spec_in; c.t_out[0] = tmp;
     CKL(h, launch_col(h->nx, COL_INV, c, 1, h->stream));
@@ -587,6 +596,7 @@ extern "C" int xfb_step(xfb_handle h, int nsteps, float dt)
     if (!h->have_state) return fail(XFB_E_STATE, "xfb_step before xfb_set_vorticity");
     CK(cudaSetDevice(h->device));
     if (h->nranks > 1) return dist_step(h, nsteps, dt);
+    if (h->generic) return generic_step(h, nsteps, dt);
     ColParams c; fill_col(h, c);
     c.jint = h->jint; c.z0 = h->z0; c.zk = h->zk; c.acc = h->acc;
     c.st_tile_stride = (long long)h->nx * h->tw_state; c.st_row_stride = h->tw_state;     // tile-major state

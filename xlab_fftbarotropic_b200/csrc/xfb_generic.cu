@@ -1,0 +1,295 @@
+// xfb_generic.cu -- grids the fused kernels do not serve (any NX, NY = 2^a 3^b 5^c up to 4096, NY even): the
+// reference's own default NPTS = 768 = 3 * 256 (src/configuration.hpp:18) lands here.
+//
+// This path keeps the reference's structure (src/main.cpp:146-317) one kernel per loop: pointwise spectral
+// operators (the bit-exact ones of xfb_api.cu), a mixed-radix Stockham line FFT in shared memory for the two
+// directions of the 2-D transforms, the Jacobian loop, the RK updates.  It is a completeness path -- small
+// grids that live in L2 -- not the roofline path; xfb_size_supported() reports 2 for it.
+// Spectral arrays are in the reference layout [NX][NY/2+1] (pitch = NY/2+1, no pair interleave, no tiling).
+#include <cstring>
+#include <vector>
+
+#include "xfb_handle.h"
+
+namespace xfb {
+
+// ---- mixed-radix Stockham FFT of `nl` lines of length n held in shared memory ---------------------------------
+// a: input lines [nl][n], b: scratch of the same size; returns the buffer that holds the result.
+// tw[k] = exp(-2 pi i k / n).  SIGN = +1: forward (e^{-i}), -1: inverse (e^{+i}), unnormalised.
+template <int SIGN>
+__device__ cpx *gen_fft(cpx *a, cpx *b, const int n, const int nl, const int *__restrict__ fac, const int nfac,
+                        const cpx *__restrict__ tw)
+{
+    int ns = 1;
+    for (int f = 0; f < nfac; ++f) {
+        const int r = fac[f], m = n / r;              // m butterflies per line
+        const int tstep = n / (ns * r);               // twiddle exp(-2 pi i s k / (ns r)) = tw[s * k * tstep]
+        for (int idx = threadIdx.x; idx < nl * m; idx += blockDim.x) {
+            const int line = idx / m, j = idx - line * m;
+            const int k = j % ns;
+            const cpx *src = a + (size_t)line * n;
+            cpx *dst = b + (size_t)line * n + (j - k) * r + k;
+            cpx x[5];
+            for (int s = 0; s < r; ++s) {
+                cpx v = src[j + s * m];
+                if (s > 0 && k > 0) {
+                    cpx w = tw[(s * k * tstep) % n];
+                    if (SIGN < 0) w.y = -w.y;
+                    v = cmul(v, w);
+                }
+                x[s] = v;
+            }
+            if (r == 2) {
+                dst[0] = cadd(x[0], x[1]);
+                dst[ns] = csub(x[0], x[1]);
+            } else if (r == 4) {
+                const cpx t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]), t2 = cadd(x[1], x[3]);
+                cpx t3 = csub(x[1], x[3]);
+                t3 = (SIGN > 0) ? mul_negi(t3) : mul_i(t3);
+                dst[0] = cadd(t0, t2);
+                dst[ns] = cadd(t1, t3);
+                dst[2 * ns] = csub(t0, t2);
+                dst[3 * ns] = csub(t1, t3);
+            } else {
+                // direct DFT of length r = 3 or 5 with the table: W_r^{q s} = tw[(q s mod r) * n / r]
+                for (int q = 0; q < r; ++q) {
+                    cpx acc = x[0];
+                    for (int s = 1; s < r; ++s) {
+                        cpx w = tw[((q * s) % r) * (n / r)];
+                        if (SIGN < 0) w.y = -w.y;
+                        acc = cadd(acc, cmul(x[s], w));
+                    }
+                    dst[q * ns] = acc;
+                }
+            }
+        }
+        __syncthreads();
+        cpx *t = a; a = b; b = t;
+        ns *= r;
+    }
+    return a;
+}
+
+struct GenParams {
+    int nx, ny, hy;
+    int nfx, nfy;
+    int facx[24], facy[24];
+    const cpx *twx, *twy;
+};
+
+// rows: real line -> half spectrum (complex transform of the real line, bins 0 .. NY/2 kept)   main.cpp:126-127,237,256
+__global__ void gen_rows_r2c(const GenParams g, const float *__restrict__ in, cpx *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    cpx *a = reinterpret_cast<cpx *>(smem), *b = a + g.ny;
+    const size_t row = blockIdx.x;
+    for (int j = threadIdx.x; j < g.ny; j += blockDim.x) a[j] = mk(in[row * g.ny + j], 0.f);
+    __syncthreads();
+    const cpx *r = gen_fft<1>(a, b, g.ny, 1, g.facy, g.nfy, g.twy);
+    for (int j = threadIdx.x; j < g.hy; j += blockDim.x) out[row * g.hy + j] = r[j];
+}
+
+// rows: half spectrum -> real line, unnormalised * scale; Im of the DC and Nyquist bins ignored like FFTW's c2r
+__global__ void gen_rows_c2r(const GenParams g, const cpx *__restrict__ in, float *__restrict__ out, const float scale)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    cpx *a = reinterpret_cast<cpx *>(smem), *b = a + g.ny;
+    const size_t row = blockIdx.x;
+    for (int j = threadIdx.x; j < g.hy; j += blockDim.x) {
+        cpx v = in[row * g.hy + j];
+        if (j == 0 || j == g.ny / 2) v.y = 0.f;
+        a[j] = v;
+        if (j > 0 && j < g.ny / 2) a[g.ny - j] = cconj(v);
+    }
+    __syncthreads();
+    const cpx *r = gen_fft<-1>(a, b, g.ny, 1, g.facy, g.nfy, g.twy);
+    for (int j = threadIdx.x; j < g.ny; j += blockDim.x) out[row * g.ny + j] = r[j].x * scale;
+}
+
+// columns: complex transform along x for a tile of w adjacent columns
+template <int SIGN>
+__global__ void gen_cols(const GenParams g, const cpx *__restrict__ in, cpx *__restrict__ out, const int w)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    cpx *a = reinterpret_cast<cpx *>(smem), *b = a + (size_t)w * g.nx;
+    const int j0 = blockIdx.x * w;
+    const int wl = (g.hy - j0 < w) ? g.hy - j0 : w;
+    for (int idx = threadIdx.x; idx < g.nx * wl; idx += blockDim.x) {
+        const int i = idx / wl, c = idx - i * wl;
+        a[(size_t)c * g.nx + i] = in[(size_t)i * g.hy + j0 + c];
+    }
+    __syncthreads();
+    const cpx *r = gen_fft<SIGN>(a, b, g.nx, wl, g.facx, g.nfx, g.twx);
+    for (int idx = threadIdx.x; idx < g.nx * wl; idx += blockDim.x) {
+        const int i = idx / wl, c = idx - i * wl;
+        out[(size_t)i * g.hy + j0 + c] = r[(size_t)c * g.nx + i];
+    }
+}
+
+// dvortdt = -u dvortdx - v dvortdy + vort_src with u already negated                              main.cpp:201,225-227
+__global__ void gen_jacobian(const float *mu, const float *zx, const float *v, const float *zy, const float *src, float *out,
+                             const long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // reference: u[i] = -u[i]; then  - u*dvortdx - v*dvortdy + src, evaluated left to right in float
+    const float u = mu[i];                        // c2r result already multiplied by -1 (negate flag)
+    float r = __fsub_rn(__fmul_rn(-u, zx[i]), __fmul_rn(v[i], zy[i]));
+    if (src) r = __fadd_rn(r, src[i]);
+    out[i] = r;
+}
+
+// rk = mask * (T + nu * lap * Z_k); RK bookkeeping exactly as the fused epilogue (xfb_colt.cuh)   main.cpp:240-251,296-312
+__global__ void gen_stage(const cpx *T, cpx *z0, cpx *zk, cpx *acc, const int nx, const int hy, const double *kx2, const double *ky2,
+                          const double mask_kd, const float nu, const float dt, const float dt_stage, const int stage)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nx * hy) return;
+    const int i = (int)(idx / hy), j = (int)(idx % hy);
+    const cpx zkv = (stage == 1) ? z0[idx] : zk[idx];
+    const float lap = lap_coe(kx2[i], ky2[j]);
+    const float tx = __fadd_rn(T[idx].x, __fmul_rn(__fmul_rn(zkv.x, lap), nu));
+    const float ty = __fadd_rn(T[idx].y, __fmul_rn(__fmul_rn(zkv.y, lap), nu));
+    const long long ii = (i <= nx / 2) ? i : nx - i;
+    const float m = ((double)(ii * ii + (long long)j * j) >= mask_kd) ? 0.0f : 1.0f;
+    const float rx = __fmul_rn(tx, m), ry = __fmul_rn(ty, m);
+    const cpx z0v = z0[idx];
+    if (stage == 4) {
+        const cpx av = acc[idx];
+        z0[idx] = mk(__fadd_rn(z0v.x, __fdiv_rn(__fmul_rn(__fadd_rn(av.x, rx), dt), 6.0f)),
+                     __fadd_rn(z0v.y, __fdiv_rn(__fmul_rn(__fadd_rn(av.y, ry), dt), 6.0f)));
+    } else {
+        if (stage == 1) acc[idx] = mk(rx, ry);
+        else {
+            const cpx av = acc[idx];
+            acc[idx] = mk(__fadd_rn(av.x, __fmul_rn(2.0f, rx)), __fadd_rn(av.y, __fmul_rn(2.0f, ry)));
+        }
+        zk[idx] = mk(__fadd_rn(z0v.x, __fmul_rn(rx, dt_stage)), __fadd_rn(z0v.y, __fmul_rn(ry, dt_stage)));
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+struct GenericPlan {
+    GenParams g;
+    cpx *twx, *twy;
+    int cols_w;
+    size_t smem_rows, smem_cols;
+};
+
+static bool factor(int n, int *fac, int *nfac)
+{
+    int k = 0;
+    while (n % 4 == 0) { fac[k++] = 4; n /= 4; }
+    while (n % 2 == 0) { fac[k++] = 2; n /= 2; }
+    while (n % 3 == 0) { fac[k++] = 3; n /= 3; }
+    while (n % 5 == 0) { fac[k++] = 5; n /= 5; }
+    *nfac = k;
+    return n == 1 && k <= 24;
+}
+
+bool generic_size_ok(int nx, int ny)
+{
+    int f[24], nf;
+    if (nx < 8 || ny < 8 || nx > 4096 || ny > 4096 || (ny & 1) || (nx & 1)) return false;
+    return factor(nx, f, &nf) && factor(ny, f, &nf);
+}
+
+static int make_table(cpx **dev, int n)
+{
+    std::vector<float2> tw(n);
+    for (int k = 0; k < n; ++k) {
+        const double a = -2.0 * M_PI * (double)k / (double)n;
+        tw[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    if (dev_alloc((void **)dev, sizeof(float2) * n)) return XFB_E_CUDA;
+    CK(cudaMemcpy(*dev, tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int generic_create(xfb_handle h)
+{
+    GenericPlan *P = new GenericPlan();
+    memset(P, 0, sizeof(*P));
+    P->g.nx = h->nx; P->g.ny = h->ny; P->g.hy = h->hy;
+    if (!factor(h->nx, P->g.facx, &P->g.nfx) || !factor(h->ny, P->g.facy, &P->g.nfy)) { delete P; return fail(XFB_E_SIZE, "bad generic size"); }
+    if (make_table(&P->twx, h->nx) || make_table(&P->twy, h->ny)) return XFB_E_CUDA;
+    P->g.twx = P->twx; P->g.twy = P->twy;
+    P->smem_rows = 2 * sizeof(cpx) * h->ny;
+    int w = 4;
+    while (w > 1 && 2 * sizeof(cpx) * (size_t)w * h->nx > 200 * 1024) --w;
+    P->cols_w = w;
+    P->smem_cols = 2 * sizeof(cpx) * (size_t)w * h->nx;
+    CK(cudaFuncSetAttribute(gen_rows_r2c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_rows));
+    CK(cudaFuncSetAttribute(gen_rows_c2r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_rows));
+    CK(cudaFuncSetAttribute(gen_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_cols));
+    CK(cudaFuncSetAttribute(gen_cols<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_cols));
+    h->generic = P;
+    return 0;
+}
+
+void generic_destroy(xfb_handle h)
+{
+    GenericPlan *P = (GenericPlan *)h->generic;
+    if (!P) return;
+    cudaFree(P->twx);
+    cudaFree(P->twy);
+    delete P;
+    h->generic = nullptr;
+}
+
+#define GLAUNCH(h, expr)                                                                          \
+    do {                                                                                          \
+        expr;                                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                     \
+        if (e__ != cudaSuccess) return fail(XFB_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+        (h)->launches++;                                                                          \
+    } while (0)
+
+int generic_fwd2d(xfb_handle h, const float *real_in, cpx *tmp, cpx *spec_out)
+{
+    GenericPlan *P = (GenericPlan *)h->generic;
+    const int tiles = (h->hy + P->cols_w - 1) / P->cols_w;
+    GLAUNCH(h, (gen_rows_r2c<<<h->nx, 128, P->smem_rows, h->stream>>>(P->g, real_in, tmp)));
+    GLAUNCH(h, (gen_cols<1><<<tiles, 256, P->smem_cols, h->stream>>>(P->g, tmp, spec_out, P->cols_w)));
+    return 0;
+}
+
+int generic_inv2d(xfb_handle h, const cpx *spec_in, cpx *tmp, float *real_out, float scale, int negate)
+{
+    GenericPlan *P = (GenericPlan *)h->generic;
+    const int tiles = (h->hy + P->cols_w - 1) / P->cols_w;
+    GLAUNCH(h, (gen_cols<-1><<<tiles, 256, P->smem_cols, h->stream>>>(P->g, spec_in, tmp, P->cols_w)));
+    GLAUNCH(h, (gen_rows_c2r<<<h->nx, 128, P->smem_rows, h->stream>>>(P->g, tmp, real_out, negate ? -scale : scale)));
+    return 0;
+}
+
+// nsteps RK4 steps, one kernel per loop of src/main.cpp:286-317
+int generic_step(xfb_handle h, int nsteps, float dt)
+{
+    const int P = h->hy;
+    const long long n = (long long)h->grids, hn = (long long)h->nx * h->hy;
+    const float scale = 1.0f / (float)((double)h->nx * (double)h->ny);
+    const unsigned gb = (unsigned)((n + 255) / 256), hb = (unsigned)((hn + 255) / 256);
+    for (int m = 0; m < h->batch; ++m) {
+        cpx *z0 = h->z0 + (size_t)m * h->hpad, *zk = h->zk + (size_t)m * h->hpad, *acc = h->acc + (size_t)m * h->hpad;
+        const float *src = h->has_src ? h->src + (size_t)m * h->grids : nullptr;
+        float *fa = h->real_a, *fb = h->real_b, *fc = h->real_c, *fd = (float *)h->t[0];      // dvortdx, dvortdy, -u, v
+        cpx *tmp = h->spec_a, *tmp2 = h->spec_b, *psi = h->t[1], *T = h->jint;
+        for (int s = 0; s < nsteps; ++s)
+            for (int k = 1; k <= 4; ++k) {
+                const cpx *z = (k == 1) ? z0 : zk;
+                if (launch_pw(h, OP_GRADX, z, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fa, scale, 0)) return XFB_E_CUDA;       // :151-154
+                if (launch_pw(h, OP_GRADY, z, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fb, scale, 0)) return XFB_E_CUDA;       // :165-168
+                if (launch_pw(h, OP_INVLAP, z, P, psi, P, P)) return XFB_E_CUDA;                                                    // :179
+                if (launch_pw(h, OP_GRADY, psi, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fc, scale, 1)) return XFB_E_CUDA;     // :198-201
+                if (launch_pw(h, OP_GRADX, psi, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fd, scale, 0)) return XFB_E_CUDA;     // :212-214
+                GLAUNCH(h, (gen_jacobian<<<gb, 256, 0, h->stream>>>(fc, fa, fd, fb, src, fa, n)));                                  // :225-227
+                if (generic_fwd2d(h, fa, tmp2, T)) return XFB_E_CUDA;                                                                // :237
+                GLAUNCH(h, (gen_stage<<<hb, 256, 0, h->stream>>>(T, z0, zk, acc, h->nx, h->hy, h->kx2, h->ky2, h->mask_kd, h->nu, dt,
+                                                                  (k == 3) ? dt : dt / 2.0f, k)));
+            }
+    }
+    return 0;
+}
+
+}  // namespace xfb

@@ -54,6 +54,7 @@ struct xfb_handle_s {
     xfb::cpx *spec_a, *spec_b;      // padded layout
     float *ref_a, *ref_b;           // reference layout half spectra (2*hgrids floats)
     long long launches;
+    void *generic;       // non-null: grid served by the generic mixed-radix path (xfb_generic.cu), reference layout everywhere
     // ---- slab decomposition (xfb_dist.cu); nranks == 1 otherwise ------------------------------------
     // rank r holds physical rows [r*rows, (r+1)*rows) and the spectral columns of panels r*nchunks ..
     // (r+1)*nchunks-1; a panel is `pitch` (= cw) columns wide, pitch_g = pitch * nranks * nchunks.
@@ -94,6 +95,14 @@ void fill_col(xfb_handle h, ColParams &p, int chunk = 0);
 int create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float nu, int batch, int device, int rank, int nranks,
                 int nchunks);
 int destroy_impl(xfb_handle h);
+
+// generic mixed-radix path (xfb_generic.cu): sizes 2^a 3^b 5^c the fused kernels do not serve, e.g. the reference's 768
+bool generic_size_ok(int nx, int ny);
+int generic_create(xfb_handle h);
+void generic_destroy(xfb_handle h);
+int generic_fwd2d(xfb_handle h, const float *real_in, cpx *tmp, cpx *spec_out);
+int generic_inv2d(xfb_handle h, const cpx *spec_in, cpx *tmp, float *real_out, float scale, int negate);
+int generic_step(xfb_handle h, int nsteps, float dt);
 
 // slab paths (xfb_dist.cu)
 int dist_set_vorticity(xfb_handle h, const float *vort_rows);
