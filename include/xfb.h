@@ -119,8 +119,8 @@ int xfb_slab_partition(int nx, int ny, int nranks, int nchunks, int rank, int *r
 int xfb_nccl_unique_id(char *id128);
 int xfb_create_dist(xfb_handle *h, int nx, int ny, float lx, float ly, float nu, int device, int rank, int nranks,
                     int nchunks, const char *id128);
-/* transport of a slab handle: 0 none (one rank), 1 grouped ncclSend/ncclRecv, 2 copy-engine pushes into the
- * peers' receive arrays mapped over CUDA IPC (default when the GPUs are peer-accessible; XFB_SLAB_NCCL=1 forces 1) */
+/* transport of a slab handle: 0 none (one rank), 1 grouped ncclSend/ncclRecv (XFB_SLAB_NCCL=1), 2 copy-engine
+ * pushes / 3 SM push kernel into the peers' receive arrays mapped over CUDA IPC (XFB_SLAB_PUSH=ce|sm) */
 int xfb_slab_transport(xfb_handle h);
 /* summed milliseconds of the all-to-all exchanges since xfb_profile(h, 1) (NCCL handles) */
 int xfb_profile_read_a2a(xfb_handle h, double *a2a_ms, long long *exchanges);

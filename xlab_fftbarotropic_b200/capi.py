@@ -264,7 +264,7 @@ class SlabBackend(Backend):
 
     @property
     def transport(self):
-        return {0: "none", 1: "nccl send/recv", 2: "p2p copy engines (CUDA IPC)"}[int(self._L.xfb_slab_transport(self._h))]
+        return {0: "none", 1: "nccl send/recv", 2: "p2p copy engines (CUDA IPC)", 3: "p2p SM push kernel (CUDA IPC)"}[int(self._L.xfb_slab_transport(self._h))]
 
     def a2a_read(self):
         ms, n = C.c_double(), C.c_longlong()

@@ -265,7 +265,11 @@ int xfb::create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float 
         for (int f = 0; f < 4; ++f) h->tr[f] = h->recv_block + (size_t)(1 + f) * h->hpad;
         if (dev_alloc((void **)&h->sync_buf, sizeof(float))) return XFB_E_CUDA;
         CK(cudaMemsetAsync(h->sync_buf, 0, sizeof(float), h->stream));
-        CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        {
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi));     // exchange work jumps the queue
+        }
         h->ncopy = 1;     // measured: several copy streams are SLOWER when the SMs keep HBM busy (tools/probes/probe_p2p_copy.cu)
         if (const char *e = getenv("XFB_SLAB_COPY_STREAMS")) h->ncopy = atoi(e) < 1 ? 1 : (atoi(e) > 4 ? 4 : atoi(e));
         for (int i = 0; i < 4; ++i) {

@@ -92,6 +92,35 @@ static inline size_t col_off(xfb_handle h, int q, int c, int r0) { return ((size
 
 enum { ROW2COL = 0, COL2ROW = 1 };
 
+// ---- SM-driven push: one launch copies up to 64 contiguous segments into peer memory with 16-byte stores ------------
+// The copy engines lose more than half of their NVLink bandwidth while the SMs keep the memory system busy
+// (tools/probes/probe_p2p_copy.cu and the slab runs: 760 -> ~300 GB/s).  A few CTAs of plain ld.global / st.global on
+// the peer mappings do not: their traffic is ordinary SM traffic.  Launched on the (high-priority) communication
+// stream the CTAs are scheduled between the compute kernel's CTAs as SMs free up.
+struct PushSegs {
+    int n;
+    const float4 *src[64];
+    float4 *dst[64];
+    unsigned long long n16[64];      // float4 elements
+};
+
+__global__ void __launch_bounds__(512) push_kernel(const PushSegs s)
+{
+    const int seg = blockIdx.y;
+    if (seg >= s.n) return;
+    const float4 *__restrict__ src = s.src[seg];
+    float4 *__restrict__ dst = s.dst[seg];
+    const unsigned long long n = s.n16[seg];
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // four independent 16-byte loads in flight per thread
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const float4 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+        dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    }
+    for (; i < n; i += stride) dst[i] = src[i];
+}
+
 // One all-to-all of the blocks (column chunks [c0, c1), local rows [r0, r1)) of `na` arrays.
 // NCCL: issued for the single local rank on `st`.  Loopback: device copies for every rank on the shared stream.
 static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *col_ptrs_of_rank, int na, int c0, int c1, int r0,
@@ -124,7 +153,40 @@ static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *
         // cut into `pieces` column ranges when there are fewer peers than streams.  Peers are visited in a rotated
         // order so that at any moment every GPU is the target of one sender.  Completion on the RECEIVER is
         // signalled by the phase barrier (phase_barrier below), not here.
+        if (h0->push_sm) {
+            PushSegs segs;
+            segs.n = 0;
+            auto add = [&](cpx *dst, const cpx *src, size_t elems) {
+                segs.src[segs.n] = reinterpret_cast<const float4 *>(src);
+                segs.dst[segs.n] = reinterpret_cast<float4 *>(dst);
+                segs.n16[segs.n] = elems / 2;
+                ++segs.n;
+            };
+            auto flush = [&]() -> int {
+                if (segs.n == 0) return 0;
+                push_kernel<<<dim3(h0->push_blocks, segs.n), 512, 0, st>>>(segs);
+                cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess) return fail(XFB_E_CUDA, "push_kernel: %s", cudaGetErrorString(e));
+                h0->launches++;
+                segs.n = 0;
+                return 0;
+            };
+            for (int i = 0; i < T->nranks; ++i) {
+                const int q = (me + i) % T->nranks;
+                cpx *peer = h0->peer_recv[q];
+                for (int c = c0; c < c1; ++c) {
+                    if (dir == ROW2COL) add(peer + col_off(h0, me, c, r0), row_ptrs_of_rank[0] + row_off(h0, q, c, r0), count);
+                    else
+                        for (int a = 0; a < na; ++a)
+                            add(peer + (size_t)(1 + a) * h0->hpad + row_off(h0, me, c, r0), col_ptrs_of_rank[a] + col_off(h0, q, c, r0), count);
+                    if (segs.n + 4 > 64)
+                        if (int e = flush()) return e;
+                }
+            }
+            return flush();
+        }
         const int ncs = h0->ncopy;
+        static const bool one_d = getenv("XFB_SLAB_1D") && atoi(getenv("XFB_SLAB_1D")) != 0;     // A/B: plain 1-D copies
         CK(cudaEventRecord(h0->ev_fork, st));
         for (int s = 0; s < ncs; ++s) CK(cudaStreamWaitEvent(h0->copy_stream[s], h0->ev_fork, 0));
         const int pieces = (T->nranks - 1 >= ncs) ? 1 : ncs / (T->nranks - 1);
@@ -142,12 +204,21 @@ static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *
                     // array 0 of the receive block = jint_recv ; chunks c0..c1-1 are rows*cw apart here, NX*cw apart there
                     const cpx *src = row_ptrs_of_rank[0] + row_off(h0, q, c0, r0) + e0;
                     cpx *dst = peer + col_off(h0, me, c0, r0) + e0;
+                    if (one_d) {
+                        for (int c = c0; c < c1; ++c)
+                            CK(cudaMemcpyAsync(dst + (size_t)(c - c0) * h0->nx * h0->pitch, src + (size_t)(c - c0) * h0->rows * h0->pitch,
+                                               wbytes, cudaMemcpyDeviceToDevice, cs));
+                    } else
                     CK(cudaMemcpy2DAsync(dst, sizeof(cpx) * (size_t)h0->nx * h0->pitch, src, sizeof(cpx) * (size_t)h0->rows * h0->pitch,
                                          wbytes, (size_t)(c1 - c0), cudaMemcpyDeviceToDevice, cs));
                 } else {
                     // arrays 1..4 of the receive block = tr[0..3] (or tr[0] alone, na == 1)
                     for (int c = c0; c < c1; ++c) {
-                        if (na == 4) {
+                        if (na == 4 && one_d) {
+                            for (int a = 0; a < 4; ++a)
+                                CK(cudaMemcpyAsync(peer + (size_t)(1 + a) * h0->hpad + row_off(h0, me, c, r0) + e0,
+                                                   col_ptrs_of_rank[a] + col_off(h0, q, c, r0) + e0, wbytes, cudaMemcpyDeviceToDevice, cs));
+                        } else if (na == 4) {
                             const cpx *src = col_ptrs_of_rank[0] + col_off(h0, q, c, r0) + e0;     // t[0]; t[1..3] follow hpad apart
                             cpx *dst = peer + h0->hpad + row_off(h0, me, c, r0) + e0;
                             CK(cudaMemcpy2DAsync(dst, sizeof(cpx) * h0->hpad, src, sizeof(cpx) * h0->hpad, wbytes, 4,
@@ -543,6 +614,12 @@ extern "C" int xfb_create_dist(xfb_handle *out, int nx, int ny, float lx, float 
         cudaMemcpyAsync(&flag, flag_d, sizeof(float), cudaMemcpyDeviceToHost, h->comm_stream);
         cudaStreamSynchronize(h->comm_stream);
         h->p2p = flag > 0.5f;
+        // who moves the bytes: copy engines, or a few CTAs of plain loads/stores (XFB_SLAB_PUSH=sm|ce).  The persistent
+        // stepper kernels (NX, NY <= 8192) leave no SM free for a concurrent push kernel, so those grids default to ce.
+        const char *push = getenv("XFB_SLAB_PUSH");
+        h->push_sm = push ? (strcmp(push, "sm") == 0) : (nx > 8192 || ny > 8192);
+        h->push_blocks = 2;     // measured on 8 GPUs at 16384^2: 1 -> 8.7, 2 -> 7.7, 4 -> 7.9 ms per step
+        if (const char *pb = getenv("XFB_SLAB_PUSH_BLOCKS")) h->push_blocks = atoi(pb) < 1 ? 1 : atoi(pb);
         cudaMemsetAsync(h->sync_buf, 0, sizeof(float), h->comm_stream);
         cudaStreamSynchronize(h->comm_stream);
     }
@@ -552,7 +629,7 @@ extern "C" int xfb_create_dist(xfb_handle *out, int nx, int ny, float lx, float 
 extern "C" int xfb_slab_transport(xfb_handle h)
 {
     if (!h || h->nranks <= 1) return 0;
-    return h->p2p ? 2 : 1;       // 2: copy-engine pushes over CUDA IPC peer mappings, 1: ncclSend/ncclRecv
+    return h->p2p ? (h->push_sm ? 3 : 2) : 1;   // 3: SM push kernel, 2: copy-engine pushes (both over CUDA IPC peer mappings), 1: ncclSend/ncclRecv
 }
 
 extern "C" int xfb_profile_read_a2a(xfb_handle h, double *a2a_ms, long long *exchanges)

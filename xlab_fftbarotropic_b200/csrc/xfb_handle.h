@@ -65,7 +65,9 @@ struct xfb_handle_s {
     xfb::cpx *t_block, *recv_block; // t[0..3] back to back ; jint_recv, tr[0..3] back to back
     xfb::cpx *peer_recv[16];        // recv_block of every rank mapped into this process (peer-to-peer over NVLink)
     float *sync_buf;                // 1 float, reduced over all ranks as the phase barrier
-    bool p2p;                       // exchange by copy-engine pushes into peer_recv (else ncclSend/ncclRecv)
+    bool p2p;                       // exchange by pushes into peer_recv (else ncclSend/ncclRecv)
+    bool push_sm;                   // p2p: pushes by an SM kernel (plain stores on the peer mappings) instead of the copy engines
+    int push_blocks;                // CTAs per segment of the push kernel
     cudaStream_t comm_stream;
     cudaStream_t copy_stream[4];    // p2p transport: the pushes of one exchange are spread over several copy engines
     cudaEvent_t ev_copy[4], ev_fork;
