@@ -34,8 +34,8 @@ struct ColTCfg {
     static constexpr int S_BYTES = NX * TW * (int)sizeof(cpx);
     static constexpr int F_BYTES = LinePlan<NX>::PADDED * FW * (int)sizeof(cpx);
     // a second staging buffer for the incoming tendency tile where it fits (NX <= 4096): the next tile is then
-    // fetched during the whole current tile.  At 8192 one buffer serves both directions (an early prefetch.global.L2
-    // of the next tile's 32-byte pieces was measured slower: it drags whole 128-byte lines through DRAM).
+    // fetched during the whole current tile.  At 8192 one buffer serves both directions (pulling the next tile
+    // into L2 early -- prefetch.global.L2 or cp.async.bulk.prefetch.tensor -- was measured SLOWER: 0.96 vs 0.92 ms).
     static constexpr bool SPLIT_IN = (2 * S_BYTES + F_BYTES + 1024 <= 227 * 1024);
     static constexpr int SMEM = (SPLIT_IN ? 2 : 1) * S_BYTES + F_BYTES + 1024;                // + alignment slack
     static constexpr int MINB = (THREADS >= 512) ? 1 : (THREADS >= 256) ? 2 : 4;

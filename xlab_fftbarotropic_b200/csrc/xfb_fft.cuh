@@ -89,6 +89,11 @@ __device__ __forceinline__ void tma_store_2d(const void *map, int x, int y, cons
                  "r"(smem_u32(src_smem))
                  : "memory");
 }
+// pull a tile towards L2 only (no shared-memory destination): exactly the box's sectors, unlike prefetch.global.L2
+__device__ __forceinline__ void tma_prefetch_2d(const void *map, int x, int y)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores have finished READING shared memory (the buffer may be overwritten)
 __device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

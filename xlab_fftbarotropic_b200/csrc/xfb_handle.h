@@ -54,6 +54,10 @@ struct xfb_handle_s {
     xfb::cpx *spec_a, *spec_b;      // padded layout
     float *ref_a, *ref_b;           // reference layout half spectra (2*hgrids floats)
     long long launches;
+    bool warmed;         // one eager step has run (kernels configured)
+    void *step_graph;    // cudaGraphExec_t of one RK4 step (8 launches), valid for graph_dt / graph_src
+    float graph_dt;
+    const void *graph_src;
     void *generic;       // non-null: grid served by the generic mixed-radix path (xfb_generic.cu), reference layout everywhere
     // ---- slab decomposition (xfb_dist.cu); nranks == 1 otherwise ------------------------------------
     // rank r holds physical rows [r*rows, (r+1)*rows) and the spectral columns of panels r*nchunks ..
