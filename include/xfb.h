@@ -97,6 +97,9 @@ int xfb_set_source(xfb_handle h, int member, const float *src);
 int xfb_step(xfb_handle h, int nsteps, float dt);
 /* record-step fields of the current state (src/main.cpp:266-282,183-222) and diagnostics */
 int xfb_get_field(xfb_handle h, int member, int which, float *out);
+/* filamentation time and deformation factor together, from one set of second derivatives of psi (the two
+ * XFB_TFIL / XFB_DEFORM calls of xfb_get_field recompute them); either output may be NULL */
+int xfb_get_diagnostics(xfb_handle h, int member, float *tfil, float *deform);
 /* effective-diffusivity histograms (README.md:6, Hendricks & Schubert 2009): per bin of the
  * tracer zeta in [cmin,cmax): area and integral of |grad zeta|^2 (float64[nbins] each, host) */
 int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cmax, double *area, double *grad2);

@@ -209,6 +209,10 @@ def test_diagnostics_against_cpu_restatement(xfb, orc):
     tfil, deform, _, _ = o.diagnostics()
     gt = b.get_field(xfb.capi.TFIL)
     gd = b.get_field(xfb.capi.DEFORM)
+    gt2, gd2 = b.diagnostics()                      # fused path: COL_DIAG + ROW_DIAG (two launches)
+    assert rel_l2(gd2, deform) < 1e-4
+    both2 = (tfil > 0) & (gt2 > 0) & (tfil < 1e6)
+    assert both2.mean() > 0.3 and rel_l2(gt2[both2], tfil[both2]) < 1e-3
     assert rel_l2(gd, deform) < 1e-4
     # tau = 2/sqrt(Q) is singular where Q -> 0+: compare where both are defined and Q is not tiny
     both = (tfil > 0) & (gt > 0) & (tfil < 1e6)

@@ -19,7 +19,7 @@ TAB_GRADX, TAB_GRADY, TAB_LAP, TAB_LAPINV, TAB_MASK = range(5)
 SYMBOLS = [
     "xfb_last_error", "xfb_create", "xfb_destroy", "xfb_sync", "xfb_gradx", "xfb_grady", "xfb_laplacian",
     "xfb_invert_laplacian", "xfb_dealias", "xfb_get_table", "xfb_r2c", "xfb_c2r", "xfb_set_vorticity",
-    "xfb_set_spectrum", "xfb_get_spectrum", "xfb_set_source", "xfb_step", "xfb_get_field", "xfb_get_keff_hist",
+    "xfb_set_spectrum", "xfb_get_spectrum", "xfb_set_source", "xfb_step", "xfb_get_field", "xfb_get_keff_hist", "xfb_get_diagnostics",
     "xfb_invert_pres", "xfb_launch_count", "xfb_stream", "xfb_size_supported", "xfb_profile", "xfb_profile_read",
     "xfb_slab_partition", "xfb_nccl_unique_id", "xfb_create_dist", "xfb_profile_read_a2a", "xfb_slab_transport",
     "xfb_loopback_create", "xfb_loopback_destroy", "xfb_loopback_set_vorticity", "xfb_loopback_set_source",
@@ -55,6 +55,7 @@ def load():
     L.xfb_set_source.argtypes = [vp, ci, vp]
     L.xfb_step.argtypes = [vp, ci, cf]
     L.xfb_get_field.argtypes = [vp, ci, ci, vp]
+    L.xfb_get_diagnostics.argtypes = [vp, ci, vp, vp]
     L.xfb_get_keff_hist.argtypes = [vp, ci, ci, cf, cf, vp, vp]
     L.xfb_invert_pres.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, cf, cf]
     L.xfb_launch_count.restype = C.c_longlong
@@ -205,6 +206,13 @@ class Backend:
             out = np.empty((self.nx, self.ny), np.float32)
         self._ck(self._L.xfb_get_field(self._h, member, which, _ptr(out)))
         return out
+
+    def diagnostics(self, member=0):
+        """-> (filamentation time, deformation factor), sharing the three second derivatives of psi"""
+        t = np.empty((self.nx, self.ny), np.float32)
+        d = np.empty((self.nx, self.ny), np.float32)
+        self._ck(self._L.xfb_get_diagnostics(self._h, member, _ptr(t), _ptr(d)))
+        return t, d
 
     def keff_hist(self, nbins, cmin, cmax, member=0):
         area = np.zeros(nbins, np.float64)

@@ -120,9 +120,20 @@ int main(int argc, char *args[])
                 std::fprintf(stderr, "main.out: %s\n", xfb_last_error());
                 return 1;
             }
-            if (diagnostics && (record("tfil", XFB_TFIL, step) || record("deform", XFB_DEFORM, step))) {
-                std::fprintf(stderr, "main.out: %s\n", xfb_last_error());
-                return 1;
+            if (diagnostics) {
+                // filamentation time and deformation factor from one set of second derivatives of psi
+                std::vector<float> deform(GRIDS);
+                if (xfb_get_diagnostics(h, 0, field.data(), deform.data()) != 0) {
+                    std::fprintf(stderr, "main.out: %s\n", xfb_last_error());
+                    return 1;
+                }
+                const char *stems[2] = {"tfil", "deform"};
+                float *bufs[2] = {field.data(), deform.data()};
+                for (int o = 0; o < 2; ++o) {
+                    std::snprintf(filename, sizeof(filename), "%s/%s_step_%d.bin", output.c_str(), stems[o], step);
+                    writeField(filename, bufs[o], GRIDS);
+                    if (log_fd) { std::fprintf(log_fd, "%s\n", filename); std::fflush(log_fd); }
+                }
             }
         }
         int chunk = 1;

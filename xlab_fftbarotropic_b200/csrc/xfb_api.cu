@@ -299,7 +299,7 @@ int xfb::destroy_impl(xfb_handle h)
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
     generic_destroy(h);
     if (h->step_graph) cudaGraphExecDestroy((cudaGraphExec_t)h->step_graph);
-    void *ptrs[] = {h->tw, h->kx, h->ky, h->kx2, h->ky2, h->z0, h->zk, h->acc, h->jint, h->t_block, h->src, h->real_a,
+    void *ptrs[] = {h->tw, h->kx, h->ky, h->kx2, h->ky2, h->z0, h->zk, h->acc, h->jint, h->t_block, h->src, h->dg, h->real_a,
                     h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b, h->recv_block, h->sync_buf};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -757,25 +757,111 @@ extern "C" int xfb_get_field(xfb_handle h, int member, int which, float *out)
     return stage_out(h, out, dout, bytes);
 }
 
+// Fused diagnostics (north_star item 4): ONE K-COL launch forms the three spectral products of the current state and
+// transforms them along x (COL_DIAG: psi_xy, psi_xx, psi_yy or zeta, zeta_x, zeta_y), ONE K-ROW launch transforms them
+// along y and combines them pointwise (ROW_DIAG) -- the stepper's TMA-staged persistent kernels with other
+// multipliers.  Replaces 6-9 pointwise passes, 3 column and 3 row transforms of the record path.
+static bool fused_diag_ok(xfb_handle h)
+{
+    static const bool off = getenv("XFB_DIAG_UNFUSED") && atoi(getenv("XFB_DIAG_UNFUSED")) != 0;
+    return !off && !h->generic && h->nranks == 1 && h->nx <= 8192 && h->ny <= 8192;
+}
+
+static int fused_diag(xfb_handle h, int member, int kind, float *out0, float *out1)
+{
+    if (!h->dg) {
+        if (dev_alloc((void **)&h->dg, 3 * sizeof(cpx) * h->hpad)) return XFB_E_CUDA;
+        CK(cudaMemsetAsync(h->dg, 0, 3 * sizeof(cpx) * h->hpad, h->stream));
+    }
+    ColParams c; fill_col(h, c);
+    c.z0 = h->z0 + (size_t)member * h->hpad; c.zk = c.z0; c.acc = c.z0; c.jint = h->jint;
+    c.st_tile_stride = (long long)h->nx * h->tw_state; c.st_row_stride = h->tw_state;
+    for (int f = 0; f < 3; ++f) c.t_out[f] = h->dg + (size_t)f * h->hpad;
+    c.t_out[3] = c.t_out[2];
+    c.stage = kind;
+    CKL(h, launch_col(h->nx, COL_DIAG, c, 1, h->stream));
+    RowParams r; fill_row(h, r, h->nx);
+    for (int f = 0; f < 3; ++f) r.spec_in[f] = h->dg + (size_t)f * h->hpad;
+    r.real_out = out0; r.real_out2 = out1; r.diag_kind = kind;
+    CKL(h, launch_row(h->ny, ROW_DIAG, r, h->stream));
+    return 0;
+}
+
+// Both strain diagnostics of one member from ONE set of the three second derivatives of psi (xfb_get_field recomputes
+// them per field): filamentation time (Rozoff et al. 2006) and deformation factor, README.md:5,7.  Either output may
+// be NULL.  Host or device pointers.
+extern "C" int xfb_get_diagnostics(xfb_handle h, int member, float *tfil, float *deform)
+{
+    if (check_member(h, member)) return XFB_E_ARG;
+    if (!tfil && !deform) return fail(XFB_E_ARG, "no output requested");
+    if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_diagnostics before xfb_set_vorticity");
+    NO_SLAB(h, "xfb_get_diagnostics");
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = sizeof(float) * h->grids;
+    const long long n = (long long)h->grids;
+    if (fused_diag_ok(h)) {
+        float *d0 = (tfil && is_device_ptr(tfil)) ? tfil : h->real_a, *d1 = (deform && is_device_ptr(deform)) ? deform : h->real_b;
+        if (fused_diag(h, member, 0, d0, d1)) return XFB_E_CUDA;
+        if (tfil && d0 != tfil) CK(cudaMemcpyAsync(tfil, d0, bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (deform && d1 != deform) CK(cudaMemcpyAsync(deform, d1, bytes, cudaMemcpyDeviceToHost, h->stream));
+        if ((tfil && d0 != tfil) || (deform && d1 != deform)) CK(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    // psi_xy -> real_b, psi_xx -> real_c, psi_yy -> real_a; each result is produced in the caller's buffer when that
+    // is device memory, else in a transform scratch array that is free by then (the input pointers are read before
+    // the output element is written, so diag_kernel may run in place)
+    if (psi_second(h, member, 0, h->real_b) || psi_second(h, member, 1, h->real_c) || psi_second(h, member, 2, h->real_a))
+        return XFB_E_CUDA;
+    float *outs[2] = {tfil, deform};
+    const int which[2] = {XFB_TFIL, XFB_DEFORM};
+    float *scratch = (float *)h->ref_a;          // 2*hgrids floats >= grids floats
+    for (int o = 0; o < 2; ++o) {
+        if (!outs[o]) continue;
+        float *d = is_device_ptr(outs[o]) ? outs[o] : scratch;
+        diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->real_b, h->real_c, h->real_a, d, n, which[o]);
+        CK(cudaGetLastError());
+        h->launches++;
+        if (d != outs[o]) {
+            CK(cudaMemcpyAsync(outs[o], d, bytes, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+    }
+    return 0;
+}
+
 // histogram of area and |grad zeta|^2 over tracer bins
 __global__ void keff_hist_kernel(const float *c, const float *gx, const float *gy, long long n, int nbins, float cmin,
                                  float scale, double da, double *area, double *grad2)
 {
+    // Most of the domain sits in one bin (zeta ~ 0 away from the vortex): a naive shared-memory atomicAdd per point
+    // serialises on that address (measured 2.6 ms at 4096^2).  Each thread therefore runs over its elements with a
+    // private (bin, count, sum) accumulator and only touches shared memory when the bin changes.
     extern __shared__ double sh[];
-    double *sa = sh, *sg = sh + nbins;
-    for (int b = threadIdx.x; b < 2 * nbins; b += blockDim.x) sh[b] = 0.0;
+    double *sg = sh;                                                   // [nbins] sum of |grad c|^2
+    unsigned long long *sc = reinterpret_cast<unsigned long long *>(sh + nbins);   // [nbins] point counts
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) { sg[b] = 0.0; sc[b] = 0ull; }
     __syncthreads();
+    int cur = -1;
+    unsigned long long cnt = 0;
+    double acc = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         int b = (int)floorf(__fmul_rn(__fsub_rn(c[i], cmin), scale));
         b = b < 0 ? 0 : (b >= nbins ? nbins - 1 : b);
-        const float g2 = __fadd_rn(__fmul_rn(gx[i], gx[i]), __fmul_rn(gy[i], gy[i]));
-        atomicAdd(&sa[b], da);
-        atomicAdd(&sg[b], (double)g2 * da);
+        const float g2 = gy ? __fadd_rn(__fmul_rn(gx[i], gx[i]), __fmul_rn(gy[i], gy[i])) : gx[i];   // gy == null: gx holds |grad c|^2
+        if (b != cur) {
+            if (cur >= 0) { atomicAdd(&sc[cur], cnt); atomicAdd(&sg[cur], acc); }
+            cur = b; cnt = 0; acc = 0.0;
+        }
+        ++cnt;
+        acc += (double)g2;
     }
+    if (cur >= 0) { atomicAdd(&sc[cur], cnt); atomicAdd(&sg[cur], acc); }
     __syncthreads();
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
-        if (sa[b] != 0.0) atomicAdd(&area[b], sa[b]);
-        if (sg[b] != 0.0) atomicAdd(&grad2[b], sg[b]);
+        if (sc[b] != 0ull) {
+            atomicAdd(&area[b], (double)sc[b] * da);
+            atomicAdd(&grad2[b], sg[b] * da);
+        }
     }
 }
 
@@ -786,14 +872,19 @@ extern "C" int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin
     if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_keff_hist before xfb_set_vorticity");
     NO_SLAB(h, "xfb_get_keff_hist");
     CK(cudaSetDevice(h->device));
-    if (derived_field(h, member, XFB_VORT, h->real_a)) return XFB_E_CUDA;
-    if (derived_field(h, member, XFB_DVORTDX, h->real_b)) return XFB_E_CUDA;
-    if (derived_field(h, member, XFB_DVORTDY, h->real_c)) return XFB_E_CUDA;
+    const bool fused = fused_diag_ok(h);
+    if (fused) {
+        if (fused_diag(h, member, 1, h->real_a, h->real_b)) return XFB_E_CUDA;       // zeta, |grad zeta|^2
+    } else {
+        if (derived_field(h, member, XFB_VORT, h->real_a)) return XFB_E_CUDA;
+        if (derived_field(h, member, XFB_DVORTDX, h->real_b)) return XFB_E_CUDA;
+        if (derived_field(h, member, XFB_DVORTDY, h->real_c)) return XFB_E_CUDA;
+    }
     double *d = (double *)h->ref_a;
     CK(cudaMemsetAsync(d, 0, sizeof(double) * 2 * nbins, h->stream));
     const double da = ((double)h->lx / h->nx) * ((double)h->ly / h->ny);
     const float scale = (float)nbins / (cmax - cmin);
-    keff_hist_kernel<<<296, 256, sizeof(double) * 2 * nbins, h->stream>>>(h->real_a, h->real_b, h->real_c, (long long)h->grids,
+    keff_hist_kernel<<<296, 256, sizeof(double) * 2 * nbins, h->stream>>>(h->real_a, h->real_b, fused ? nullptr : h->real_c, (long long)h->grids,
                                                                            nbins, cmin, scale, da, d, d + nbins);
     CK(cudaGetLastError());
     h->launches++;

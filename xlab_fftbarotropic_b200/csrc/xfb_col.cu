@@ -80,8 +80,9 @@ static int launch_colt_t(const ColParams &p, int batch, cudaStream_t st)
     } else {
         maps.jint = CUtensorMap();
     }
-    for (int f = 0; f < 4; ++f)
+    for (int f = 0; f < (MODE == COL_DIAG ? 3 : 4); ++f)
         if (int e = make_pair_map(&maps.t[f], p.t_out[f], rows, p.pitch, C::TW, C::BOXR)) return e;
+    if (MODE == COL_DIAG) maps.t[3] = maps.t[2];
     const int tiles_per_member = p.pitch / C::TW, tiles_total = tiles_per_member * batch;
     const int blocks = tiles_total < resident ? tiles_total : resident;
     colt_kernel<NX, MODE><<<blocks, C::THREADS, C::SMEM, st>>>(p, maps, tiles_per_member, tiles_total);
@@ -124,9 +125,10 @@ static int launch_colt_n(int mode, const ColParams &p, int batch, cudaStream_t s
         // opt-in: measured SLOWER than colt_kernel<8192> (1.14 vs 0.92 ms per launch at 8192^2): the DSMEM
         // redistribution and ten cluster barriers per tile cost more than the re-reads and the late fetch they remove
         static const bool cluster = env_int("XFB_COL_CLUSTER", 0) != 0;
-        if (cluster)
+        if (cluster && mode != COL_DIAG)
             return mode == COL_STEP ? launch_coltc_t<NX, COL_STEP>(p, batch, st) : launch_coltc_t<NX, COL_PRO>(p, batch, st);
     }
+    if (mode == COL_DIAG) return launch_colt_t<NX, COL_DIAG>(p, batch, st);
     return mode == COL_STEP ? launch_colt_t<NX, COL_STEP>(p, batch, st) : launch_colt_t<NX, COL_PRO>(p, batch, st);
 }
 
@@ -161,7 +163,8 @@ int launch_col(int nx, int mode, const ColParams &p, int batch, cudaStream_t st)
 {
     // the stepper's modes run on the TMA-staged persistent kernel (XFB_COL_GEN1=1: first-generation kernel, A/B knob)
     static const bool gen1 = env_int("XFB_COL_GEN1", 0) != 0;
-    if ((mode == COL_STEP || mode == COL_PRO) && !gen1) {
+    if (mode == COL_DIAG && (gen1 || nx > 8192)) return (int)cudaErrorNotSupported;
+    if ((mode == COL_STEP || mode == COL_PRO || mode == COL_DIAG) && !gen1) {
         switch (nx) {
         case 256: return launch_colt_n<256>(mode, p, batch, st);
         case 512: return launch_colt_n<512>(mode, p, batch, st);

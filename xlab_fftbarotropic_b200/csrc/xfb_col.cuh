@@ -16,7 +16,7 @@
 
 namespace xfb {
 
-enum { COL_FWD = 0, COL_INV = 1, COL_STEP = 2, COL_PRO = 3 };
+enum { COL_FWD = 0, COL_INV = 1, COL_STEP = 2, COL_PRO = 3, COL_DIAG = 4 };
 
 struct ColParams {
     const cpx *jint;      // FWD/STEP: y-transformed lines, pair layout (see xfb_row.cuh): (i, j) at ((i>>1)*pitch + j)*2 + (i&1)

@@ -187,14 +187,15 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
         }
 
         // ------------------------------------------------------------------ prologue of the next stage + 4 inverse
-        const cpx *zsrc = (MODE == COL_PRO || p.stage == 4) ? p.z0 : p.zk;
-        if (KEEP && MODE == COL_PRO) {
+        const cpx *zsrc = (MODE == COL_PRO || MODE == COL_DIAG || p.stage == 4) ? p.z0 : p.zk;
+        constexpr int NF = (MODE == COL_DIAG) ? 3 : 4;
+        if (KEEP && (MODE == COL_PRO || MODE == COL_DIAG)) {
             const size_t e0 = moff + (size_t)tl * (size_t)p.st_tile_stride + (size_t)t[0] * srow + c[0];
 #pragma unroll
             for (int k = 0; k < 16; ++k) zkeep[k] = zsrc[e0 + (size_t)(k * G) * srow];
         }
 #pragma unroll 1
-        for (int f = 0; f < 4; ++f) {
+        for (int f = 0; f < NF; ++f) {
 #pragma unroll 1
             for (int cg = 0; cg < NG; ++cg) {
                 const int col = cg * FW + c[0];
@@ -211,6 +212,22 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
                     const int i = t[0] + k * G;
                     const cpx z = KEEP ? zkeep[k] : v[0][k];
                     const float kx = (float)signed_row<NX>(t[0], k) * p.kxscale;
+                    if (MODE == COL_DIAG) {
+                        // p.stage 0: psi_xy, psi_xx, psi_yy = (kx ky, kx^2, ky^2) Z / (kx^2+ky^2)   [(i kx)(i ky) Z/-(k^2) ...]
+                        // p.stage 1: zeta, zeta_x, zeta_y   = (1, i kx, i ky) Z
+                        if (p.stage == 0) {
+                            const float k2 = (i == 0 && j == 0) ? 1.0f : fmaf(kx, kx, ky2);
+                            const float num = (f == 0) ? kx * ky : (f == 1) ? kx * kx : ky2;
+                            const float rr = __fdividef(num, k2);
+                            v[0][k] = mk(z.y * rr, z.x * rr);            // swap(rr z)
+                        } else if (f == 0) {
+                            v[0][k] = mk(z.y, z.x);
+                        } else {
+                            const float kk = (f == 1) ? kx : ky;
+                            v[0][k] = mk(z.x * kk, -z.y * kk);       // swap(i kk z)
+                        }
+                        continue;
+                    }
                     // f = 0: i kx Z, 1: i ky Z, 2: i ky Psi (u before negation), 3: i kx Psi (v);
                     // Psi = Z / -(kx^2+ky^2), (0,0) entry divides by 1                 (fftwfop.cpp:43,112-117)
                     float kk = (f == 0 || f == 3) ? kx : ky;

@@ -54,6 +54,7 @@ struct xfb_handle_s {
     xfb::cpx *spec_a, *spec_b;      // padded layout
     float *ref_a, *ref_b;           // reference layout half spectra (2*hgrids floats)
     long long launches;
+    xfb::cpx *dg;        // 3 exchange arrays of the fused diagnostics path, allocated on first use
     bool warmed;         // one eager step has run (kernels configured)
     void *step_graph;    // cudaGraphExec_t of one RK4 step (8 launches), valid for graph_dt / graph_src
     float graph_dt;

@@ -35,7 +35,7 @@ template <int NY, int MODE, bool DIST>
 static int launch_pair_t(const RowParams &p, cudaStream_t st)
 {
     typedef PairCfg<NY> C;
-    constexpr int smem = (MODE == ROW_JAC) ? C::SMEM_JAC : C::SMEM;
+    constexpr int smem = (MODE == ROW_JAC || MODE == ROW_DIAG) ? C::SMEM_JAC : C::SMEM;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(rowpair_kernel<NY, MODE, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -44,7 +44,7 @@ static int launch_pair_t(const RowParams &p, cudaStream_t st)
     }
     const int npairs = p.nrows / 2;
     int blocks = (npairs + C::PPC - 1) / C::PPC;
-    if (MODE == ROW_JAC && !DIST) {
+    if ((MODE == ROW_JAC || MODE == ROW_DIAG) && !DIST) {
         // persistent: as many CTAs as are resident at once, each walks over pair groups
         static int resident = 0;
         if (resident == 0) {
@@ -77,6 +77,7 @@ static int launch_row_n(int mode, const RowParams &p, cudaStream_t st)
             case ROW_R2C: return dist ? launch_pair_t<NY, ROW_R2C, true>(p, st) : launch_pair_t<NY, ROW_R2C, false>(p, st);
             case ROW_C2R: return dist ? launch_pair_t<NY, ROW_C2R, true>(p, st) : launch_pair_t<NY, ROW_C2R, false>(p, st);
             case ROW_JAC: return dist ? launch_pair_t<NY, ROW_JAC, true>(p, st) : launch_pair_t<NY, ROW_JAC, false>(p, st);
+            case ROW_DIAG: return dist ? (int)cudaErrorInvalidValue : launch_pair_t<NY, ROW_DIAG, false>(p, st);
             }
             return (int)cudaErrorInvalidValue;
         }

@@ -21,13 +21,15 @@
 
 namespace xfb {
 
-enum { ROW_R2C = 0, ROW_C2R = 1, ROW_JAC = 2 };
+enum { ROW_R2C = 0, ROW_C2R = 1, ROW_JAC = 2, ROW_DIAG = 3 };
 
 struct RowParams {
     const cpx *spec_in[4];   // JAC: T_zx, T_zy, T_u, T_v ; C2R: [0]
     const float *real_in;    // R2C input ; JAC: optional source term (may be null)
     cpx *spec_out;           // R2C / JAC output (y-transformed lines)
-    float *real_out;         // C2R output
+    float *real_out;         // C2R output ; DIAG: first output field
+    float *real_out2;        // DIAG: second output field
+    int diag_kind;           // DIAG: 0 strain diagnostics (tfil, deform) of psi_xy, psi_xx, psi_yy ; 1 tracer (zeta, |grad zeta|^2)
     const cpx *tw;           // exp(-2 pi i k / twn)
     int twn;
     int nrows;               // NX * batch

@@ -232,6 +232,80 @@ rowpair_kernel(const RowParams p)
         }
     } else if (DIST) {
         jac_pair_direct<NY, DIST>(p, smem_raw, sm, lane_pair, t, off, roff, live, tw, bar);
+    } else if (MODE == ROW_DIAG) {
+        // ---- diagnostics: three inverse transforms per row pair and a pointwise combine, same TMA-staged persistent
+        // machinery as the Jacobian below.  kind 0: (psi_xy, psi_xx, psi_yy) -> filamentation time 2/sqrt(S1^2+S2^2-zeta^2)
+        // (Rozoff et al. 2006) and deformation factor (README.md:5,7); kind 1: (zeta, zeta_x, zeta_y) -> zeta and
+        // |grad zeta|^2 for the effective-diffusivity histograms (README.md:6, Hendricks & Schubert 2009).
+        __shared__ unsigned long long mbar_all[C::PPC];
+        unsigned long long *mbar = &mbar_all[lane_pair];
+        if (t == 0) {
+            mbar_init(mbar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        const unsigned bytes = (unsigned)(2 * p.pitch * sizeof(cpx));
+        const int ngroups = (npairs + C::PPC - 1) / C::PPC;
+        unsigned phase = 0;
+        cpx *park0 = reinterpret_cast<cpx *>(smem_raw) + (size_t)C::PPC * LinePlan<NY>::PADDED + (size_t)lane_pair * (2 * NY);
+        const cpx *const f0 = p.spec_in[0], *const f1 = p.spec_in[1], *const f2 = p.spec_in[2];
+        const size_t pair_stride = (size_t)(2 * p.pitch);
+#define XFB_PAIR_OF(g_) (((g_) * C::PPC + lane_pair < npairs) ? ((g_) * C::PPC + lane_pair) : (npairs - 1))
+#define XFB_FETCH(base_, pr_)                                                   \
+    do {                                                                        \
+        if (t == 0) {                                                           \
+            mbar_expect_tx(mbar, bytes);                                        \
+            bulk_g2s(sm, (base_) + (size_t)(pr_) * pair_stride, bytes, mbar);   \
+        }                                                                       \
+    } while (0)
+        int g = blockIdx.x;
+        if (g < ngroups) XFB_FETCH(f0, XFB_PAIR_OF(g));
+        for (; g < ngroups; g += gridDim.x) {
+            const int pr = XFB_PAIR_OF(g);
+            const size_t ro = (size_t)pr * (size_t)(2 * NY);
+#pragma unroll 1
+            for (int f = 0; f < 3; ++f) {
+                mbar_wait(mbar, phase);
+                phase ^= 1;
+                c2r_pair_staged<NY, Bar, true>(v, sm, t, tw, bar);
+                if (f < 2) XFB_FETCH((f == 0) ? f1 : f2, pr);
+                else {
+                    const int gn = g + gridDim.x;
+                    if (gn < ngroups) XFB_FETCH(f0, XFB_PAIR_OF(gn));
+                }
+                if (f < 2) {
+                    cpx *park = park0 + f * NY;
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) park[q * G + t] = mk(v[q].y * p.scale, v[q].x * p.scale);
+                }
+            }
+            float *oa = p.real_out + ro, *ob = oa + NY, *o2a = p.real_out2 + ro, *o2b = o2a + NY;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const cpx a0 = park0[q * G + t], a1 = park0[NY + q * G + t];
+                const cpx a2 = mk(v[q].y * p.scale, v[q].x * p.scale);
+                float r0[2], r1[2];
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const float x0 = w ? a0.y : a0.x, x1 = w ? a1.y : a1.x, x2 = w ? a2.y : a2.x;
+                    if (p.diag_kind == 0) {
+                        // S1 = -2 psi_xy, S2 = psi_xx - psi_yy, zeta = psi_xx + psi_yy          (diag_kernel, xfb_api.cu)
+                        const float s1 = __fmul_rn(-2.0f, x0), s2 = __fsub_rn(x1, x2), z = __fadd_rn(x1, x2);
+                        const float ss = __fadd_rn(__fmul_rn(s1, s1), __fmul_rn(s2, s2)), zz = __fmul_rn(z, z);
+                        const float qq = __fsub_rn(ss, zz), den = __fadd_rn(ss, zz);
+                        r0[w] = (qq > 0.0f) ? __fdiv_rn(2.0f, __fsqrt_rn(qq)) : 0.0f;
+                        r1[w] = (den > 0.0f) ? __fdiv_rn(qq, den) : 0.0f;
+                    } else {
+                        r0[w] = x0;
+                        r1[w] = __fadd_rn(__fmul_rn(x1, x1), __fmul_rn(x2, x2));
+                    }
+                }
+                oa[t + q * G] = r0[0]; ob[t + q * G] = r0[1];
+                o2a[t + q * G] = r1[0]; o2b[t + q * G] = r1[1];
+            }
+        }
+#undef XFB_FETCH
+#undef XFB_PAIR_OF
     } else {
         // ---- persistent, TMA-staged: CTA g handles pair groups g, g + gridDim.x, ...  Every spectral line pair is
         // fetched by ONE cp.async.bulk into the FFT buffer (free at that moment) and the fetch of the next field is
