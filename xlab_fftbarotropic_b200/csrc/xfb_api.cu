@@ -520,6 +520,9 @@ extern "C" int xfb_c2r(xfb_handle h, const float *spec_in, float *real_out)
 // ------------------------------------------------------------------------------------------------
 // stepper tier
 // ------------------------------------------------------------------------------------------------
+static bool fused_diag_ok(xfb_handle h);
+static int fused_products(xfb_handle h, int member, int kind, int nfields);
+
 static int check_member(xfb_handle h, int member)
 {
     if (!h) return fail(XFB_E_ARG, "null handle");
@@ -535,9 +538,20 @@ extern "C" int xfb_set_vorticity(xfb_handle h, int member, const float *vort)
     if (h->nranks > 1) return dist_set_vorticity(h, vort);
     const void *din;
     if (stage_in(h, vort, h->real_a, sizeof(float) * h->grids, &din)) return XFB_E_CUDA;
-    if (fwd2d(h, (const float *)din, h->spec_a, h->spec_b)) return XFB_E_CUDA;
-    if (launch_pw(h, OP_COPY, h->spec_b, h->pitch, h->z0 + (size_t)member * h->hpad, h->pitch, h->pitch, 0, h->tw_state))
-        return XFB_E_CUDA;
+    if (fused_diag_ok(h)) {
+        // y pass (pair kernel) then the TMA-staged x pass straight into the tile-major state
+        RowParams r; fill_row(h, r, h->nx);
+        r.real_in = (const float *)din; r.spec_out = h->spec_a;
+        CKL(h, launch_row(h->ny, ROW_R2C, r, h->stream));
+        ColParams c; fill_col(h, c);
+        c.jint = h->spec_a; c.z0 = h->z0 + (size_t)member * h->hpad; c.zk = c.z0; c.acc = c.z0;
+        c.st_tile_stride = (long long)h->nx * h->tw_state; c.st_row_stride = h->tw_state;
+        CKL(h, launch_col(h->nx, COL_FWDT, c, 1, h->stream));
+    } else {
+        if (fwd2d(h, (const float *)din, h->spec_a, h->spec_b)) return XFB_E_CUDA;
+        if (launch_pw(h, OP_COPY, h->spec_b, h->pitch, h->z0 + (size_t)member * h->hpad, h->pitch, h->pitch, 0, h->tw_state))
+            return XFB_E_CUDA;
+    }
     h->have_state = true;
     h->tf_valid = false;
     if (!is_device_ptr(vort)) CK(cudaStreamSynchronize(h->stream));
@@ -673,6 +687,15 @@ static int derived_field(xfb_handle h, int member, int which, float *dout)
     const cpx *z = h->z0 + (size_t)member * h->hpad;
     const float scale = 1.0f / (float)((double)h->nx * (double)h->ny);
     const int P = h->pitch, T = h->tw_state;
+    if (fused_diag_ok(h)) {
+        // record fields on the stepper's kernels: one K-COL launch (spectral multiplier + x pass, TMA-staged) and one
+        // K-ROW launch (y pass, normalisation, sign); multipliers in float32 (<= 2 ulp from the operator tier's tables)
+        if (fused_products(h, member, 2 + which, 1)) return XFB_E_CUDA;
+        RowParams r; fill_row(h, r, h->nx);
+        r.spec_in[0] = h->dg; r.real_out = dout; r.scale = scale; r.negate = (which == XFB_U) ? 1 : 0;
+        CKL(h, launch_row(h->ny, ROW_C2R, r, h->stream));
+        return 0;
+    }
     switch (which) {
     case XFB_VORT:
         if (launch_pw(h, OP_COPY, z, P, h->spec_a, P, P, T, 0)) return XFB_E_CUDA;
@@ -763,11 +786,15 @@ extern "C" int xfb_get_field(xfb_handle h, int member, int which, float *out)
 // multipliers.  Replaces 6-9 pointwise passes, 3 column and 3 row transforms of the record path.
 static bool fused_diag_ok(xfb_handle h)
 {
-    static const bool off = getenv("XFB_DIAG_UNFUSED") && atoi(getenv("XFB_DIAG_UNFUSED")) != 0;
+    // the A/B knobs that select the first-generation kernels also select the unfused record path
+    static const bool off = (getenv("XFB_DIAG_UNFUSED") && atoi(getenv("XFB_DIAG_UNFUSED")) != 0) ||
+                            (getenv("XFB_COL_GEN1") && atoi(getenv("XFB_COL_GEN1")) != 0) ||
+                            (getenv("XFB_ROW_SINGLE") && atoi(getenv("XFB_ROW_SINGLE")) != 0);
     return !off && !h->generic && h->nranks == 1 && h->nx <= 8192 && h->ny <= 8192;
 }
 
-static int fused_diag(xfb_handle h, int member, int kind, float *out0, float *out1)
+// K-COL half: `nfields` spectral products of member's state, x-inverse-transformed into h->dg[0 .. nfields-1]
+static int fused_products(xfb_handle h, int member, int kind, int nfields)
 {
     if (!h->dg) {
         if (dev_alloc((void **)&h->dg, 3 * sizeof(cpx) * h->hpad)) return XFB_E_CUDA;
@@ -776,10 +803,16 @@ static int fused_diag(xfb_handle h, int member, int kind, float *out0, float *ou
     ColParams c; fill_col(h, c);
     c.z0 = h->z0 + (size_t)member * h->hpad; c.zk = c.z0; c.acc = c.z0; c.jint = h->jint;
     c.st_tile_stride = (long long)h->nx * h->tw_state; c.st_row_stride = h->tw_state;
-    for (int f = 0; f < 3; ++f) c.t_out[f] = h->dg + (size_t)f * h->hpad;
-    c.t_out[3] = c.t_out[2];
+    for (int f = 0; f < 4; ++f) c.t_out[f] = h->dg + (size_t)(f < 3 ? f : 2) * h->hpad;
     c.stage = kind;
+    c.nfields = nfields;
     CKL(h, launch_col(h->nx, COL_DIAG, c, 1, h->stream));
+    return 0;
+}
+
+static int fused_diag(xfb_handle h, int member, int kind, float *out0, float *out1)
+{
+    if (fused_products(h, member, kind, 3)) return XFB_E_CUDA;
     RowParams r; fill_row(h, r, h->nx);
     for (int f = 0; f < 3; ++f) r.spec_in[f] = h->dg + (size_t)f * h->hpad;
     r.real_out = out0; r.real_out2 = out1; r.diag_kind = kind;

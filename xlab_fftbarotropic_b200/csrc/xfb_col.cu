@@ -75,14 +75,19 @@ static int launch_colt_t(const ColParams &p, int batch, cudaStream_t st)
     }
     ColTMaps maps;
     const long long rows = (long long)NX * batch;
-    if (MODE == COL_STEP) {
+    if (MODE == COL_STEP || MODE == COL_FWDT) {
         if (int e = make_pair_map(&maps.jint, p.jint, rows, p.pitch, C::TW, C::BOXR)) return e;
     } else {
         maps.jint = CUtensorMap();
     }
-    for (int f = 0; f < (MODE == COL_DIAG ? 3 : 4); ++f)
-        if (int e = make_pair_map(&maps.t[f], p.t_out[f], rows, p.pitch, C::TW, C::BOXR)) return e;
-    if (MODE == COL_DIAG) maps.t[3] = maps.t[2];
+    const int nout = (MODE == COL_FWDT) ? 0 : (MODE == COL_DIAG) ? p.nfields : 4;
+    for (int f = 0; f < 4; ++f) {
+        if (f < nout) {
+            if (int e = make_pair_map(&maps.t[f], p.t_out[f], rows, p.pitch, C::TW, C::BOXR)) return e;
+        } else {
+            maps.t[f] = (f > 0 && nout > 0) ? maps.t[0] : CUtensorMap();
+        }
+    }
     const int tiles_per_member = p.pitch / C::TW, tiles_total = tiles_per_member * batch;
     const int blocks = tiles_total < resident ? tiles_total : resident;
     colt_kernel<NX, MODE><<<blocks, C::THREADS, C::SMEM, st>>>(p, maps, tiles_per_member, tiles_total);
@@ -125,10 +130,11 @@ static int launch_colt_n(int mode, const ColParams &p, int batch, cudaStream_t s
         // opt-in: measured SLOWER than colt_kernel<8192> (1.14 vs 0.92 ms per launch at 8192^2): the DSMEM
         // redistribution and ten cluster barriers per tile cost more than the re-reads and the late fetch they remove
         static const bool cluster = env_int("XFB_COL_CLUSTER", 0) != 0;
-        if (cluster && mode != COL_DIAG)
+        if (cluster && (mode == COL_STEP || mode == COL_PRO))
             return mode == COL_STEP ? launch_coltc_t<NX, COL_STEP>(p, batch, st) : launch_coltc_t<NX, COL_PRO>(p, batch, st);
     }
     if (mode == COL_DIAG) return launch_colt_t<NX, COL_DIAG>(p, batch, st);
+    if (mode == COL_FWDT) return launch_colt_t<NX, COL_FWDT>(p, batch, st);
     return mode == COL_STEP ? launch_colt_t<NX, COL_STEP>(p, batch, st) : launch_colt_t<NX, COL_PRO>(p, batch, st);
 }
 
@@ -163,8 +169,8 @@ int launch_col(int nx, int mode, const ColParams &p, int batch, cudaStream_t st)
 {
     // the stepper's modes run on the TMA-staged persistent kernel (XFB_COL_GEN1=1: first-generation kernel, A/B knob)
     static const bool gen1 = env_int("XFB_COL_GEN1", 0) != 0;
-    if (mode == COL_DIAG && (gen1 || nx > 8192)) return (int)cudaErrorNotSupported;
-    if ((mode == COL_STEP || mode == COL_PRO || mode == COL_DIAG) && !gen1) {
+    if ((mode == COL_DIAG || mode == COL_FWDT) && (gen1 || nx > 8192)) return (int)cudaErrorNotSupported;
+    if ((mode == COL_STEP || mode == COL_PRO || mode == COL_DIAG || mode == COL_FWDT) && !gen1) {
         switch (nx) {
         case 256: return launch_colt_n<256>(mode, p, batch, st);
         case 512: return launch_colt_n<512>(mode, p, batch, st);

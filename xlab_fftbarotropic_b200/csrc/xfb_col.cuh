@@ -16,7 +16,7 @@
 
 namespace xfb {
 
-enum { COL_FWD = 0, COL_INV = 1, COL_STEP = 2, COL_PRO = 3, COL_DIAG = 4 };
+enum { COL_FWD = 0, COL_INV = 1, COL_STEP = 2, COL_PRO = 3, COL_DIAG = 4, COL_FWDT = 5 };
 
 struct ColParams {
     const cpx *jint;      // FWD/STEP: y-transformed lines, pair layout (see xfb_row.cuh): (i, j) at ((i>>1)*pitch + j)*2 + (i&1)
@@ -47,7 +47,8 @@ struct ColParams {
     float nu;
     float dt;             // full step
     float dt_stage;       // dt/2, dt/2, dt for stages 1..3
-    int stage;            // 1..4
+    int stage;            // 1..4 ; COL_DIAG: product set (0 strain, 1 tracer, 2 + field id: one record field)
+    int nfields;          // COL_DIAG: number of products (3 or 1)
 };
 
 template <int NX, int W>

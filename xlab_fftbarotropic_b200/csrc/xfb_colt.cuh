@@ -79,8 +79,9 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
     // element (row i = t + k*G, tile column col) of S: ((i >> 1) * TW + col) * 2 + (i & 1); k-stride = G * TW
     const int s_base = ((t[0] >> 1) * TW) * 2 + (t[0] & 1);
 
+    constexpr bool HAS_FWD = (MODE == COL_STEP || MODE == COL_FWDT);
     int tile = blockIdx.x;
-    if (MODE == COL_STEP && tile < tiles_total && tid == 0) {
+    if (HAS_FWD && tile < tiles_total && tid == 0) {
         const int member = tile / tiles_per_member, tl = tile - member * tiles_per_member;
         mbar_expect_tx(&full, C::S_BYTES);
 #pragma unroll 1
@@ -97,9 +98,9 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
         cpx zkeep[KEEP ? 16 : 1];
 
         // ------------------------------------------------------------------ forward + epilogue
-        if (MODE == COL_STEP) {
+        if (HAS_FWD) {
             // epilogue operands of this tile towards L2 (needed after the forward transform)
-            {
+            if (MODE == COL_STEP) {
                 const size_t e = moff + (size_t)(tl * NG) * (size_t)p.st_tile_stride;
                 const int bytes = NX * TW * (int)sizeof(cpx);
                 for (int o = tid * 128; o < bytes; o += C::THREADS * 128) {
@@ -124,6 +125,12 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
                 const float ky2 = kyv * kyv;
                 const size_t soff = moff + (size_t)(tl * NG + cg) * (size_t)p.st_tile_stride;
                 const size_t e0 = soff + (size_t)t[0] * srow + c[0];
+                if (MODE == COL_FWDT) {
+                    // plain forward transform of the tile into the tile-major state (xfb_set_vorticity: main.cpp:256)
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) p.z0[e0 + (size_t)(k * G) * srow] = v[0][k];
+                    continue;
+                }
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     cpx z0v[8], zkv[8], av[8];
@@ -174,7 +181,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
             }
         }
 
-        if (MODE == COL_STEP && C::SPLIT_IN) {
+        if (HAS_FWD && C::SPLIT_IN) {
             // every thread has read SI (it is behind the forward transform's barriers): fetch the next tile now
             const int nt = tile + gridDim.x;
             if (nt < tiles_total && tid == 0) {
@@ -188,7 +195,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
 
         // ------------------------------------------------------------------ prologue of the next stage + 4 inverse
         const cpx *zsrc = (MODE == COL_PRO || MODE == COL_DIAG || p.stage == 4) ? p.z0 : p.zk;
-        constexpr int NF = (MODE == COL_DIAG) ? 3 : 4;
+        const int NF = (MODE == COL_FWDT) ? 0 : (MODE == COL_DIAG) ? p.nfields : 4;
         if (KEEP && (MODE == COL_PRO || MODE == COL_DIAG)) {
             const size_t e0 = moff + (size_t)tl * (size_t)p.st_tile_stride + (size_t)t[0] * srow + c[0];
 #pragma unroll
@@ -220,11 +227,25 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
                             const float num = (f == 0) ? kx * ky : (f == 1) ? kx * kx : ky2;
                             const float rr = __fdividef(num, k2);
                             v[0][k] = mk(z.y * rr, z.x * rr);            // swap(rr z)
-                        } else if (f == 0) {
-                            v[0][k] = mk(z.y, z.x);
+                        } else if (p.stage == 1) {
+                            if (f == 0) v[0][k] = mk(z.y, z.x);
+                            else {
+                                const float kk = (f == 1) ? kx : ky;
+                                v[0][k] = mk(z.x * kk, -z.y * kk);       // swap(i kk z)
+                            }
                         } else {
-                            const float kk = (f == 1) ? kx : ky;
-                            v[0][k] = mk(z.x * kk, -z.y * kk);       // swap(i kk z)
+                            // one record field: 0 vort, 1 psi, 2 u (negated after the y pass), 3 v, 7 dvortdx, 8 dvortdy
+                            const int w = p.stage - 2;
+                            const float li = (i == 0 && j == 0) ? 1.0f : -fmaf(kx, kx, ky2);
+                            if (w == 0) v[0][k] = mk(z.y, z.x);
+                            else if (w == 1) {
+                                const float rr = __fdividef(1.0f, li);
+                                v[0][k] = mk(z.y * rr, z.x * rr);
+                            } else {
+                                float kk = (w == 3 || w == 7) ? kx : ky;
+                                if (w == 2 || w == 3) kk = __fdividef(kk, li);
+                                v[0][k] = mk(z.x * kk, -z.y * kk);
+                            }
                         }
                         continue;
                     }
@@ -256,7 +277,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
         }
 
         // single staging buffer: next tile's tendency into S as soon as the last store has read it
-        if (MODE == COL_STEP && !C::SPLIT_IN) {
+        if (HAS_FWD && !C::SPLIT_IN) {
             const int nt = tile + gridDim.x;
             if (nt < tiles_total && tid == 0) {
                 const int nm = nt / tiles_per_member, ntl = nt - nm * tiles_per_member;
