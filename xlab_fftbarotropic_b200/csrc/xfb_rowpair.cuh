@@ -350,21 +350,23 @@ rowpair_kernel(const RowParams p)
                 c2r_pair_staged<NY, Bar, true>(v, sm, t, tw, bar);
                 if (f < 3) XFB_FETCH((f == 0) ? f_zx : (f == 1) ? f_tv : f_zy, pr);      // order T_u, T_zx, T_v, T_zy
                 cpx *park = park0 + (f >> 1) * NY;
-                if (f & 1) {
+                if (f == 1) {
 #pragma unroll
                     for (int q = 0; q < 16; ++q) {
                         const cpx a = park[q * G + t];
                         park[q * G + t] = mk(a.x * (v[q].y * p.scale), a.y * (v[q].x * p.scale));
                     }
-                } else {
+                } else if (f != 3) {
 #pragma unroll
                     for (int q = 0; q < 16; ++q) park[q * G + t] = mk(v[q].y * p.scale, v[q].x * p.scale);
                 }
             }
+            // f = 3 left dvortdy in v: J = (-u dvortdx) - v dvortdy straight from the two parks (main.cpp:225-227)
             cpx J[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-                const cpx j1 = park0[q * G + t], j2 = park0[NY + q * G + t];
+                const cpx j1 = park0[q * G + t], b = park0[NY + q * G + t];
+                const cpx j2 = mk(b.x * (v[q].y * p.scale), b.y * (v[q].x * p.scale));
                 J[q] = mk(j1.x - j2.x, j1.y - j2.y);
             }
             if (p.real_in != nullptr) {
