@@ -97,6 +97,13 @@ int xfb_set_source(xfb_handle h, int member, const float *src);
 int xfb_step(xfb_handle h, int nsteps, float dt);
 /* record-step fields of the current state (src/main.cpp:266-282,183-222) and diagnostics */
 int xfb_get_field(xfb_handle h, int member, int which, float *out);
+/* asynchronous record output: the field is formed on the handle's stream and copied to a PINNED host buffer
+ * (xfb_host_alloc) on a second stream; the call returns at once and later xfb_step calls overlap the copy.
+ * xfb_wait_field(ticket) blocks until that buffer is complete.  Up to 8 fields in flight. */
+int xfb_host_alloc(float **p, size_t nfloats);
+int xfb_host_free(float *p);
+int xfb_get_field_async(xfb_handle h, int member, int which, float *pinned_out, int *ticket);
+int xfb_wait_field(xfb_handle h, int ticket);
 /* filamentation time and deformation factor together, from one set of second derivatives of psi (the two
  * XFB_TFIL / XFB_DEFORM calls of xfb_get_field recompute them); either output may be NULL */
 int xfb_get_diagnostics(xfb_handle h, int member, float *tfil, float *deform);

@@ -270,3 +270,36 @@ def test_large_grid_properties(xfb, n):
     ens1 = float((np.abs(z1.astype(np.complex128)) ** 2 * w).sum())
     assert ens1 <= ens0 * (1 + 1e-6)
     b.close()
+
+
+def test_async_record_fields_match_blocking_reads(xfb):
+    """xfb_get_field_async: fields travel to pinned buffers on a second stream while stepping continues; the values
+    are those of the state at the time of the call"""
+    import ctypes as C
+    n = 512
+    b = xfb.Backend(n)
+    b.set_vorticity(fields.kuo2004(n))
+    b.step(2, 3.0)
+    want = {w: b.get_field(w) for w in (xfb.capi.VORT, xfb.capi.PSI, xfb.capi.U, xfb.capi.V, xfb.capi.SRC)}
+    L = b._L
+    bufs, tickets = {}, {}
+    for w in want:
+        p = C.c_void_p()
+        assert L.xfb_host_alloc(C.byref(p), n * n) == 0
+        bufs[w] = p
+        tickets[w] = b.get_field_async(w, p.value)
+    b.step(5, 3.0)                                      # overlaps the copies; must not change what was recorded
+    for w in want:
+        b.wait_field(tickets[w])
+        got = np.ctypeslib.as_array(C.cast(bufs[w], C.POINTER(C.c_float)), shape=(n, n))
+        assert np.array_equal(got, want[w]), w
+    # more requests than slots: the ring recycles
+    p0 = bufs[xfb.capi.VORT]
+    ts = [b.get_field_async(xfb.capi.VORT, p0.value) for _ in range(20)]
+    b.wait_field(ts[-1])
+    b.wait_field(ts[0])
+    with pytest.raises(xfb.XfbError):
+        b.wait_field(10 ** 6)
+    for p in bufs.values():
+        assert L.xfb_host_free(p) == 0
+    b.close()

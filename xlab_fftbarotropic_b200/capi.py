@@ -20,6 +20,7 @@ SYMBOLS = [
     "xfb_last_error", "xfb_create", "xfb_destroy", "xfb_sync", "xfb_gradx", "xfb_grady", "xfb_laplacian",
     "xfb_invert_laplacian", "xfb_dealias", "xfb_get_table", "xfb_r2c", "xfb_c2r", "xfb_set_vorticity",
     "xfb_set_spectrum", "xfb_get_spectrum", "xfb_set_source", "xfb_step", "xfb_get_field", "xfb_get_keff_hist", "xfb_get_diagnostics",
+    "xfb_host_alloc", "xfb_host_free", "xfb_get_field_async", "xfb_wait_field",
     "xfb_invert_pres", "xfb_launch_count", "xfb_stream", "xfb_size_supported", "xfb_profile", "xfb_profile_read",
     "xfb_slab_partition", "xfb_nccl_unique_id", "xfb_create_dist", "xfb_profile_read_a2a", "xfb_slab_transport",
     "xfb_loopback_create", "xfb_loopback_destroy", "xfb_loopback_set_vorticity", "xfb_loopback_set_source",
@@ -56,6 +57,10 @@ def load():
     L.xfb_step.argtypes = [vp, ci, cf]
     L.xfb_get_field.argtypes = [vp, ci, ci, vp]
     L.xfb_get_diagnostics.argtypes = [vp, ci, vp, vp]
+    L.xfb_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.xfb_host_free.argtypes = [vp]
+    L.xfb_get_field_async.argtypes = [vp, ci, ci, vp, C.POINTER(ci)]
+    L.xfb_wait_field.argtypes = [vp, ci]
     L.xfb_get_keff_hist.argtypes = [vp, ci, ci, cf, cf, vp, vp]
     L.xfb_invert_pres.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, cf, cf]
     L.xfb_launch_count.restype = C.c_longlong
@@ -206,6 +211,15 @@ class Backend:
             out = np.empty((self.nx, self.ny), np.float32)
         self._ck(self._L.xfb_get_field(self._h, member, which, _ptr(out)))
         return out
+
+    def get_field_async(self, which, pinned_ptr, member=0):
+        """enqueue field -> pinned host buffer (address from xfb_host_alloc); returns a ticket for wait_field"""
+        t = C.c_int()
+        self._ck(self._L.xfb_get_field_async(self._h, member, which, C.c_void_p(pinned_ptr), C.byref(t)))
+        return t.value
+
+    def wait_field(self, ticket):
+        self._ck(self._L.xfb_wait_field(self._h, ticket))
 
     def diagnostics(self, member=0):
         """-> (filamentation time, deformation factor), sharing the three second derivatives of psi"""

@@ -9,14 +9,22 @@
 //   -n <NPTS=768> -d <dt=3> -t <total_steps=1200> -r <record_step=100> -L <600000> -N <NU=6.5>
 // Additions: -g <cuda device>, -D (also write filamentation time / deformation factor at record steps),
 //   -q (no per-step line).
+// Record output is asynchronous: at a record step the five fields are formed on the GPU and copied
+// to pinned host buffers on a second stream (xfb_get_field_async) while the next stretch of steps already runs; a
+// writer thread waits for each buffer, calls writeField and appends the `log` line -- same files, same order as the
+// reference (main.cpp:266-282,183-222).
 // All arithmetic runs on the GPU through the C ABI (include/xfb.h); this file is I/O and control only.
 #include <getopt.h>
 #include <unistd.h>
 
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/xfb.h"
@@ -97,12 +105,59 @@ int main(int argc, char *args[])
     std::printf("Initialization complete.\n");
     CHECK(xfb_set_vorticity(h, 0, field.data()));                  // step 01, main.cpp:256
 
-    auto record = [&](const char *stem, int which, int step) -> int {
-        if (xfb_get_field(h, 0, which, field.data()) != 0) return 1;
+    // ---- asynchronous record output: one pinned buffer per field kind, a writer thread, jobs in log order
+    struct Job { int ticket; float *buf; std::string file; };
+    std::deque<Job> jobs;
+    std::mutex mu;
+    std::condition_variable cv_jobs, cv_idle;
+    bool closing = false, writer_failed = false;
+    int pending = 0;
+    std::thread writer([&]() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_jobs.wait(lk, [&] { return closing || !jobs.empty(); });
+                if (jobs.empty()) return;
+                j = jobs.front();
+                jobs.pop_front();
+            }
+            if (xfb_wait_field(h, j.ticket) != 0) writer_failed = true;
+            writeField(j.file.c_str(), j.buf, GRIDS);
+            if (log_fd) { std::fprintf(log_fd, "%s\n", j.file.c_str()); std::fflush(log_fd); }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                --pending;
+            }
+            cv_idle.notify_all();
+        }
+    });
+    auto wait_writer = [&]() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_idle.wait(lk, [&] { return pending == 0; });
+    };
+    const int NKIND = 7;
+    float *pinned[NKIND] = {nullptr};
+    auto record = [&](int kind, const char *stem, int which, int step) -> int {
+        if (!pinned[kind] && xfb_host_alloc(&pinned[kind], GRIDS) != 0) return 1;
+        int ticket = -1;
+        if (xfb_get_field_async(h, 0, which, pinned[kind], &ticket) != 0) return 1;
         std::snprintf(filename, sizeof(filename), "%s/%s_step_%d.bin", output.c_str(), stem, step);
-        writeField(filename, field.data(), GRIDS);
-        if (log_fd) { std::fprintf(log_fd, "%s\n", filename); std::fflush(log_fd); }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            jobs.push_back(Job{ticket, pinned[kind], filename});
+            ++pending;
+        }
+        cv_jobs.notify_one();
         return 0;
+    };
+    auto shutdown_writer = [&]() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            closing = true;
+        }
+        cv_jobs.notify_all();
+        writer.join();
     };
 
     int step = 0;
@@ -114,26 +169,14 @@ int main(int argc, char *args[])
             std::printf("\n");
         }
         if (record_flag) {
+            wait_writer();                     // the pinned buffers of the previous record step are on disk
             // same order as the reference's log: source, vort (main.cpp:268-278), then psi, u, v (:183-222)
-            if (record("vort_src_input", XFB_SRC, step) || record("vort", XFB_VORT, step) ||
-                record("psi", XFB_PSI, step) || record("u", XFB_U, step) || record("v", XFB_V, step)) {
+            if (record(0, "vort_src_input", XFB_SRC, step) || record(1, "vort", XFB_VORT, step) ||
+                record(2, "psi", XFB_PSI, step) || record(3, "u", XFB_U, step) || record(4, "v", XFB_V, step) ||
+                (diagnostics && (record(5, "tfil", XFB_TFIL, step) || record(6, "deform", XFB_DEFORM, step)))) {
                 std::fprintf(stderr, "main.out: %s\n", xfb_last_error());
+                shutdown_writer();
                 return 1;
-            }
-            if (diagnostics) {
-                // filamentation time and deformation factor from one set of second derivatives of psi
-                std::vector<float> deform(GRIDS);
-                if (xfb_get_diagnostics(h, 0, field.data(), deform.data()) != 0) {
-                    std::fprintf(stderr, "main.out: %s\n", xfb_last_error());
-                    return 1;
-                }
-                const char *stems[2] = {"tfil", "deform"};
-                float *bufs[2] = {field.data(), deform.data()};
-                for (int o = 0; o < 2; ++o) {
-                    std::snprintf(filename, sizeof(filename), "%s/%s_step_%d.bin", output.c_str(), stems[o], step);
-                    writeField(filename, bufs[o], GRIDS);
-                    if (log_fd) { std::fprintf(log_fd, "%s\n", filename); std::fflush(log_fd); }
-                }
             }
         }
         int chunk = 1;
@@ -145,12 +188,27 @@ int main(int argc, char *args[])
                 for (int s = step + 1; s < step + chunk; ++s) std::printf("# Step %d, time = %.2f\n", s, s * dt);
         } else {
             const int got = vs_reader.read(step * dt, src.data());       // main-shallow-water.cpp:304
-            if (got == 1) CHECK(xfb_set_source(h, 0, src.data()));
+            if (got == 1 && xfb_set_source(h, 0, src.data()) != 0) {
+                std::fprintf(stderr, "main.out: %s\n", xfb_last_error());
+                shutdown_writer();
+                return 1;
+            }
         }
-        CHECK(xfb_step(h, chunk, dt));
+        if (xfb_step(h, chunk, dt) != 0) {
+            std::fprintf(stderr, "main.out: %s\n", xfb_last_error());
+            shutdown_writer();
+            return 1;
+        }
         step += chunk;
     }
-    CHECK(xfb_sync(h));
+    const int sync_rc = xfb_sync(h);
+    wait_writer();
+    shutdown_writer();
+    if (sync_rc != 0 || writer_failed) {
+        std::fprintf(stderr, "main.out: %s\n", xfb_last_error());
+        return 1;
+    }
+    for (int k = 0; k < NKIND; ++k) xfb_host_free(pinned[k]);
     if (log_fd) std::fclose(log_fd);
     xfb_destroy(h);
     std::printf("Program ends. Congrats!\n");

@@ -299,6 +299,15 @@ int xfb::destroy_impl(xfb_handle h)
     if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
     generic_destroy(h);
     if (h->step_graph) cudaGraphExecDestroy((cudaGraphExec_t)h->step_graph);
+    if (h->rec_stream) {
+        cudaStreamSynchronize(h->rec_stream);
+        for (int i = 0; i < XFB_NREC; ++i) {
+            cudaEventDestroy(h->rec_ready[i]);
+            cudaEventDestroy(h->rec_done[i]);
+            if (h->rec_buf[i]) cudaFree(h->rec_buf[i]);
+        }
+        cudaStreamDestroy(h->rec_stream);
+    }
     void *ptrs[] = {h->tw, h->kx, h->ky, h->kx2, h->ky2, h->z0, h->zk, h->acc, h->jint, h->t_block, h->src, h->dg, h->real_a,
                     h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b, h->recv_block, h->sync_buf};
     for (void *p : ptrs)
@@ -522,6 +531,7 @@ extern "C" int xfb_c2r(xfb_handle h, const float *spec_in, float *real_out)
 // ------------------------------------------------------------------------------------------------
 static bool fused_diag_ok(xfb_handle h);
 static int fused_products(xfb_handle h, int member, int kind, int nfields);
+static int fused_diag(xfb_handle h, int member, int kind, float *out0, float *out1);
 
 static int check_member(xfb_handle h, int member)
 {
@@ -745,26 +755,17 @@ __global__ void diag_kernel(const float *pxy, const float *pxx, const float *pyy
     else out[i] = (den > 0.0f) ? __fdiv_rn(q, den) : 0.0f;
 }
 
-extern "C" int xfb_get_field(xfb_handle h, int member, int which, float *out)
+// field `which` of member into the DEVICE buffer dout (grids floats), on the handle's stream
+static int field_to_device(xfb_handle h, int member, int which, float *dout)
 {
-    if (check_member(h, member)) return XFB_E_ARG;
-    if (!out) return fail(XFB_E_ARG, "null output");
-    if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_field before xfb_set_vorticity");
-    CK(cudaSetDevice(h->device));
-    if (h->nranks > 1 && which != XFB_SRC) return dist_get_field(h, which, out);
     const size_t bytes = sizeof(float) * h->grids;
     if (which == XFB_SRC) {
-        if (!h->src) {
-            if (is_device_ptr(out)) { CK(cudaMemsetAsync(out, 0, bytes, h->stream)); }
-            else memset(out, 0, bytes);
-            return 0;
-        }
-        CK(cudaMemcpyAsync(out, h->src + (size_t)member * h->grids, bytes,
-                           is_device_ptr(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        if (!h->src) { CK(cudaMemsetAsync(dout, 0, bytes, h->stream)); return 0; }
+        CK(cudaMemcpyAsync(dout, h->src + (size_t)member * h->grids, bytes, cudaMemcpyDeviceToDevice, h->stream));
         return 0;
     }
-    float *dout = (float *)stage_out_target(out, h->real_a);
+    if ((which == XFB_TFIL || which == XFB_DEFORM) && fused_diag_ok(h))
+        return fused_diag(h, member, 0, which == XFB_TFIL ? dout : h->real_a, which == XFB_DEFORM ? dout : h->real_b);
     if (which == XFB_TFIL || which == XFB_DEFORM) {
         if (psi_second(h, member, 0, h->real_b)) return XFB_E_CUDA;
         if (psi_second(h, member, 1, h->real_c)) return XFB_E_CUDA;
@@ -774,10 +775,75 @@ extern "C" int xfb_get_field(xfb_handle h, int member, int which, float *out)
         diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->real_b, h->real_c, pyy, dout, n, which);
         CK(cudaGetLastError());
         h->launches++;
-    } else {
-        if (derived_field(h, member, which, dout)) return XFB_E_CUDA;
+        return 0;
     }
+    return derived_field(h, member, which, dout);
+}
+
+extern "C" int xfb_get_field(xfb_handle h, int member, int which, float *out)
+{
+    if (check_member(h, member)) return XFB_E_ARG;
+    if (!out) return fail(XFB_E_ARG, "null output");
+    if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_field before xfb_set_vorticity");
+    CK(cudaSetDevice(h->device));
+    if (h->nranks > 1 && which != XFB_SRC) return dist_get_field(h, which, out);
+    const size_t bytes = sizeof(float) * h->grids;
+    if (which == XFB_SRC && !h->src && !is_device_ptr(out)) { memset(out, 0, bytes); return 0; }
+    float *dout = (float *)stage_out_target(out, h->real_a);
+    if (field_to_device(h, member, which, dout)) return XFB_E_CUDA;
+    if (which == XFB_SRC && dout == out) { CK(cudaStreamSynchronize(h->stream)); return 0; }
     return stage_out(h, out, dout, bytes);
+}
+
+// ---- asynchronous record output: the fields of the current state travel to pinned host buffers on a second stream
+// while the caller goes on stepping (src/main.cpp:266-282,183-222 overlapped with the following steps) --------------
+extern "C" int xfb_host_alloc(float **p, size_t nfloats)
+{
+    if (!p) return fail(XFB_E_ARG, "null pointer");
+    CK(cudaMallocHost((void **)p, sizeof(float) * nfloats));
+    return 0;
+}
+
+extern "C" int xfb_host_free(float *p)
+{
+    if (p) CK(cudaFreeHost(p));
+    return 0;
+}
+
+extern "C" int xfb_get_field_async(xfb_handle h, int member, int which, float *pinned_out, int *ticket)
+{
+    if (check_member(h, member)) return XFB_E_ARG;
+    if (!pinned_out || !ticket) return fail(XFB_E_ARG, "null argument");
+    if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_field_async before xfb_set_vorticity");
+    NO_SLAB(h, "xfb_get_field_async");
+    CK(cudaSetDevice(h->device));
+    if (!h->rec_stream) {
+        CK(cudaStreamCreateWithFlags(&h->rec_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < XFB_NREC; ++i) {
+            CK(cudaEventCreateWithFlags(&h->rec_ready[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->rec_done[i], cudaEventDisableTiming));
+        }
+    }
+    const int slot = h->rec_next % XFB_NREC;
+    if (h->rec_next >= XFB_NREC) CK(cudaEventSynchronize(h->rec_done[slot]));        // the slot's previous copy has left
+    if (!h->rec_buf[slot] && dev_alloc((void **)&h->rec_buf[slot], sizeof(float) * h->grids)) return XFB_E_CUDA;
+    if (field_to_device(h, member, which, h->rec_buf[slot])) return XFB_E_CUDA;
+    CK(cudaEventRecord(h->rec_ready[slot], h->stream));
+    CK(cudaStreamWaitEvent(h->rec_stream, h->rec_ready[slot], 0));
+    CK(cudaMemcpyAsync(pinned_out, h->rec_buf[slot], sizeof(float) * h->grids, cudaMemcpyDeviceToHost, h->rec_stream));
+    CK(cudaEventRecord(h->rec_done[slot], h->rec_stream));
+    *ticket = h->rec_next++;
+    return 0;
+}
+
+extern "C" int xfb_wait_field(xfb_handle h, int ticket)
+{
+    if (!h) return fail(XFB_E_ARG, "null handle");
+    if (ticket < 0 || ticket >= h->rec_next) return fail(XFB_E_ARG, "bad ticket %d", ticket);
+    if (h->rec_next - ticket > XFB_NREC) return 0;              // its slot has been reused: that copy completed long ago
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->rec_done[ticket % XFB_NREC]));
+    return 0;
 }
 
 // Fused diagnostics (north_star item 4): ONE K-COL launch forms the three spectral products of the current state and

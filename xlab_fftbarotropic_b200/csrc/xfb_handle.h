@@ -30,6 +30,8 @@ struct Team;
 
 }  // namespace xfb
 
+#define XFB_NREC 8          // record fields in flight (xfb_get_field_async)
+
 struct xfb_handle_s {
     int nx, ny, hy, pitch, batch, device;
     int tw_state;        // column tile width = tile-major layout of z0/zk/acc
@@ -54,6 +56,10 @@ struct xfb_handle_s {
     xfb::cpx *spec_a, *spec_b;      // padded layout
     float *ref_a, *ref_b;           // reference layout half spectra (2*hgrids floats)
     long long launches;
+    cudaStream_t rec_stream;                     // device -> pinned host copies of xfb_get_field_async
+    float *rec_buf[XFB_NREC];
+    cudaEvent_t rec_ready[XFB_NREC], rec_done[XFB_NREC];
+    int rec_next;
     xfb::cpx *dg;        // 3 exchange arrays of the fused diagnostics path, allocated on first use
     bool warmed;         // one eager step has run (kernels configured)
     void *step_graph;    // cudaGraphExec_t of one RK4 step (8 launches), valid for graph_dt / graph_src
