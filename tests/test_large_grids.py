@@ -6,7 +6,8 @@ size-independent properties of the reference algorithm, and agreement of the ker
     the circle untouched (the mask is applied to the tendency only, main.cpp:296-312).
   * KAT-5 invariants: mode (0,0) is constant, enstrophy does not grow.
   * the second-generation kernels (rowpair / colt, TMA-staged, persistent) must reproduce the first-generation
-    ones (XFB_ROW_SINGLE=1 XFB_COL_GEN1=1) and the cluster variant (XFB_COL_CLUSTER=1) to float32 rounding: the
+    ones (XFB_ROW_SINGLE=1 XFB_COL_GEN1=1), the TMEM-park variant of K-ROW (XFB_ROW_TMEM=1) and the cluster variant of
+    K-COL (XFB_COL_CLUSTER=1) to float32 rounding: the
     knobs are read once per process, so each variant runs in its own interpreter.
   * one step at 2048^2 against the CPU oracle (the largest size the oracle finishes in a few seconds).
 """
@@ -100,7 +101,7 @@ def _run_variant(n, dt, env, out):
 def test_kernel_generations_agree(n, dt, tmp_path):
     ref = _run_variant(n, dt, {}, str(tmp_path / "default.npy"))
     assert np.isfinite(ref.view(np.float32)).all()
-    variants = [{"XFB_ROW_SINGLE": "1", "XFB_COL_GEN1": "1"}]
+    variants = [{"XFB_ROW_SINGLE": "1", "XFB_COL_GEN1": "1"}, {"XFB_ROW_TMEM": "1"}]
     if n == 8192:
         variants.append({"XFB_COL_CLUSTER": "1"})
     for env in variants:

@@ -100,6 +100,58 @@ __device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bul
 // all committed bulk stores are complete (global memory written)
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- tensor memory (TMEM) as thread-private scratch ------------------------------------------------------------
+// 256 KB per SM next to the register file, reached with tcgen05.ld / tcgen05.st (SASS LDTM / STTM).  The .32x32b
+// shape maps thread i of a warp to lane 32*(warp%4)+i and register r to column col+r: every thread owns a private row,
+// which is exactly what "parking" 32 registers needs -- without touching the shared-memory pipe the FFT exchanges
+// saturate.  One warp allocates `COLS` columns (power of two >= 32) for the CTA and frees them at the end.
+template <int COLS>
+__device__ __forceinline__ unsigned tmem_alloc_cta(unsigned *slot_smem)
+{
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "n"(COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *slot_smem;
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_free_cta(unsigned base)
+{
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(COLS) : "memory");
+}
+// 16 complex registers <-> 32 columns of this thread's TMEM row
+__device__ __forceinline__ void tmem_park(unsigned taddr, const cpx (&r)[16])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "f"(r[0].x), "f"(r[0].y), "f"(r[1].x), "f"(r[1].y), "f"(r[2].x), "f"(r[2].y), "f"(r[3].x), "f"(r[3].y), "f"(r[4].x), "f"(r[4].y),
+        "f"(r[5].x), "f"(r[5].y), "f"(r[6].x), "f"(r[6].y), "f"(r[7].x), "f"(r[7].y), "f"(r[8].x), "f"(r[8].y), "f"(r[9].x), "f"(r[9].y),
+        "f"(r[10].x), "f"(r[10].y), "f"(r[11].x), "f"(r[11].y), "f"(r[12].x), "f"(r[12].y), "f"(r[13].x), "f"(r[13].y), "f"(r[14].x),
+        "f"(r[14].y), "f"(r[15].x), "f"(r[15].y)
+        : "memory");
+}
+// the stores above complete asynchronously; a load of what they wrote waits for them first
+__device__ __forceinline__ void tmem_unpark(unsigned taddr, cpx (&r)[16])
+{
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=f"(r[0].x), "=f"(r[0].y), "=f"(r[1].x), "=f"(r[1].y), "=f"(r[2].x), "=f"(r[2].y), "=f"(r[3].x), "=f"(r[3].y), "=f"(r[4].x),
+          "=f"(r[4].y), "=f"(r[5].x), "=f"(r[5].y), "=f"(r[6].x), "=f"(r[6].y), "=f"(r[7].x), "=f"(r[7].y), "=f"(r[8].x), "=f"(r[8].y),
+          "=f"(r[9].x), "=f"(r[9].y), "=f"(r[10].x), "=f"(r[10].y), "=f"(r[11].x), "=f"(r[11].y), "=f"(r[12].x), "=f"(r[12].y),
+          "=f"(r[13].x), "=f"(r[13].y), "=f"(r[14].x), "=f"(r[14].y), "=f"(r[15].x), "=f"(r[15].y)
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 #define XFB_C8 0.70710678118654752440f
 #define XFB_C16 0.92387953251128675613f
 #define XFB_S16 0.38268343236508977173f

@@ -60,6 +60,37 @@ static int launch_pair_t(const RowParams &p, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
+// ROW_JAC with TMEM parks and double-buffered staging: opt-in (XFB_ROW_TMEM=1).  Correct, but measured SLOWER than the
+// shared-memory parks (8192^2: 0.62 vs 0.58 ms per launch, 4096^2: 0.16 vs 0.13): the extra live state (TMEM
+// addresses, two-buffer bookkeeping) pushes the transform core over 128 registers (300 bytes of spills per thread).
+template <int NY>
+static int launch_pair_tmem(const RowParams &p, cudaStream_t st)
+{
+    typedef PairTCfg<NY> C;
+    static int resident = 0;
+    if (resident == 0) {
+        cudaError_t e = cudaFuncSetAttribute(rowpair_jac_tmem_kernel<NY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rowpair_jac_tmem_kernel<NY>, C::THREADS, C::SMEM);
+        if (per_sm * C::TCOLS > 512) per_sm = 512 / C::TCOLS;            // TMEM columns are a per-SM resource too
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int npairs = p.nrows / 2;
+    int blocks = (npairs + C::PPC - 1) / C::PPC;
+    if (blocks > resident) blocks = resident;
+    rowpair_jac_tmem_kernel<NY><<<blocks, C::THREADS, C::SMEM, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+static bool use_tmem_parks()
+{
+    static const bool on = getenv("XFB_ROW_TMEM") && atoi(getenv("XFB_ROW_TMEM")) != 0;
+    return on;
+}
+
 // XFB_ROW_SINGLE=1 forces the one-row-per-line kernel (tuning / A-B knob); 16384 always uses it
 static bool use_pair_kernel(int ny)
 {
@@ -76,7 +107,9 @@ static int launch_row_n(int mode, const RowParams &p, cudaStream_t st)
             switch (mode) {
             case ROW_R2C: return dist ? launch_pair_t<NY, ROW_R2C, true>(p, st) : launch_pair_t<NY, ROW_R2C, false>(p, st);
             case ROW_C2R: return dist ? launch_pair_t<NY, ROW_C2R, true>(p, st) : launch_pair_t<NY, ROW_C2R, false>(p, st);
-            case ROW_JAC: return dist ? launch_pair_t<NY, ROW_JAC, true>(p, st) : launch_pair_t<NY, ROW_JAC, false>(p, st);
+            case ROW_JAC:
+                if (!dist && use_tmem_parks()) return launch_pair_tmem<NY>(p, st);
+                return dist ? launch_pair_t<NY, ROW_JAC, true>(p, st) : launch_pair_t<NY, ROW_JAC, false>(p, st);
             case ROW_DIAG: return dist ? (int)cudaErrorInvalidValue : launch_pair_t<NY, ROW_DIAG, false>(p, st);
             }
             return (int)cudaErrorInvalidValue;

@@ -192,6 +192,148 @@ __device__ __forceinline__ void jac_pair_direct(const RowParams &p, unsigned cha
     r2c_pair<NY, DIST>(J, p.spec_out + off, p, live ? p.pitch : 0, sm, t, tw, bar);
 }
 
+// ---- ROW_JAC with the parked products in TENSOR MEMORY and a double-buffered staging area -----------------------------
+// The parked products are thread-private (a thread reads back exactly what it wrote), so they do not need shared
+// memory at all: each thread keeps them in its own TMEM row (tcgen05.st / tcgen05.ld, 2 x 32 columns).  That takes
+// 2 * NY * 8 bytes per pair out of shared memory (131 KB at NY = 8192) and a sixth of the traffic off the shared-memory
+// pipe, and the freed space holds TWO staging buffers: the bulk fetch of field n+2 is issued as soon as field n has
+// been read, a whole transform ahead, so no fetch latency is exposed any more.
+// STATUS: correct (tests pass with XFB_ROW_TMEM=1), measured slower than the shared-memory parks -- see xfb_row.cu.
+template <int NY>
+struct PairTCfg {
+    static constexpr int G = NY / 16;
+    static constexpr int THREADS = (G >= 128) ? G : 128;
+    static constexpr int PPC = THREADS / G;
+    static constexpr int ST_ELEMS = 2 * (NY / 2 + 4);                     // complex elements of one pair region
+    static constexpr int F_BYTES = PPC * LinePlan<NY>::PADDED * (int)sizeof(cpx);
+    static constexpr int ST_BYTES = PPC * ST_ELEMS * (int)sizeof(cpx);    // one staging buffer, all pairs of the CTA
+    static constexpr int SMEM = F_BYTES + 2 * ST_BYTES;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TCOLS = (WARPS > 8) ? 256 : (WARPS > 4) ? 128 : 64;     // 64 columns per group of four warps
+    static constexpr int MINB = (THREADS >= 512) ? 1 : (THREADS >= 256) ? 2 : 4;
+};
+
+template <int NY>
+__global__ void __launch_bounds__(PairTCfg<NY>::THREADS, PairTCfg<NY>::MINB)
+rowpair_jac_tmem_kernel(const RowParams p)
+{
+    typedef PairTCfg<NY> C;
+    constexpr int G = C::G;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ unsigned tmem_slot;
+    __shared__ unsigned long long mbar_all[2 * C::PPC];
+    const int lane_pair = threadIdx.x / G;
+    const int t = threadIdx.x % G;
+    cpx *sm = reinterpret_cast<cpx *>(smem_raw) + (size_t)lane_pair * LinePlan<NY>::PADDED;
+    // staging buffer b of this pair slot: stage0 + b * (ST_BYTES / sizeof(cpx))
+    cpx *const stage0 = reinterpret_cast<cpx *>(smem_raw + C::F_BYTES) + (size_t)lane_pair * C::ST_ELEMS;
+    constexpr int ST_STRIDE = C::ST_BYTES / (int)sizeof(cpx);
+    unsigned long long *mbar = &mbar_all[2 * lane_pair];
+    const int npairs = p.nrows >> 1;
+
+    LineTw<NY> tw;
+    tw.init(p.tw, p.twn, t);
+    typedef typename RowBarSel<(G >= 32 && C::PPC > 1)>::type Bar;
+    const Bar bar = RowBarSel<(G >= 32 && C::PPC > 1)>::make(1 + lane_pair, G);
+
+    if (t == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_fence_init();
+    }
+    const unsigned tbase = tmem_alloc_cta<C::TCOLS>(&tmem_slot);          // includes a CTA barrier
+    const int warp = threadIdx.x >> 5;
+    const unsigned park0 = tbase + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 64), park1 = park0 + 32;
+
+    const int ngroups = (npairs + C::PPC - 1) / C::PPC;
+    const int my_groups = (blockIdx.x < ngroups) ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int nfetch = 4 * my_groups;
+    // fetch number n of this pair slot: pair group blockIdx.x + (n / 4) * gridDim.x, field n % 4 (T_u, T_zx, T_v, T_zy),
+    // buffer n & 1
+#define XFB_PAIR_OF(g_) (((g_) * C::PPC + lane_pair < npairs) ? ((g_) * C::PPC + lane_pair) : (npairs - 1))
+#define XFB_FETCH(n_)                                                                                                  \
+    do {                                                                                                               \
+        const int nn_ = (n_);                                                                                          \
+        if (t == 0 && nn_ < nfetch) {                                                                                  \
+            const int pr_ = XFB_PAIR_OF((int)blockIdx.x + (nn_ >> 2) * (int)gridDim.x);                                \
+            const int fi_ = nn_ & 3;                                                                                   \
+            const cpx *base_ = (fi_ == 0) ? p.spec_in[2] : (fi_ == 1) ? p.spec_in[0] : (fi_ == 2) ? p.spec_in[3] : p.spec_in[1]; \
+            mbar_expect_tx(mbar + (nn_ & 1), (unsigned)(2 * p.pitch * sizeof(cpx)));                                   \
+            bulk_g2s(stage0 + (nn_ & 1) * ST_STRIDE, base_ + (size_t)pr_ * (size_t)(2 * p.pitch),                      \
+                     (unsigned)(2 * p.pitch * sizeof(cpx)), mbar + (nn_ & 1));                                         \
+        }                                                                                                              \
+    } while (0)
+    XFB_FETCH(0);
+    XFB_FETCH(1);
+    unsigned phase = 0;      // bit b: parity to wait for on buffer b
+    cpx v[16];
+    int n = 0;
+    for (int gi = 0; gi < my_groups; ++gi) {
+        const int g = blockIdx.x + gi * gridDim.x;
+        const int pr = XFB_PAIR_OF(g);
+        const bool alive = g * C::PPC + lane_pair < npairs;
+        const size_t po = (size_t)pr * (size_t)(2 * p.pitch), ro = (size_t)pr * (size_t)(2 * NY);
+#pragma unroll 1
+        for (int f = 0; f < 4; ++f, ++n) {
+            const int b = n & 1;
+            mbar_wait(mbar + b, (phase >> b) & 1);
+            phase ^= 1u << b;
+            {
+                const float4 *st = reinterpret_cast<const float4 *>(stage0 + b * ST_STRIDE);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int pos = t + (8 * h + e) * G;
+                        const int m = (h == 0) ? pos : NY - pos;
+                        float4 x = st[m];
+                        if ((h == 0 && e == 0 && pos == 0) || (h == 1 && e == 0 && pos == NY / 2)) { x.y = 0.f; x.w = 0.f; }
+                        v[8 * h + e] = (h == 0) ? mk(x.y + x.z, x.x - x.w) : mk(x.z - x.y, x.x + x.w);
+                    }
+                }
+            }
+            bar.sync();                 // everyone has read this staging buffer: refill it two fields ahead
+            XFB_FETCH(n + 2);
+            line_fft<NY, 1>(v, sm, t, 0, tw, bar);
+            // v = (b[n], a[n]) unscaled, swapped: .y is row 2m, .x row 2m+1
+            if (f == 0) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = mk(v[q].y * p.scale, v[q].x * p.scale);      // -u
+                tmem_park(park0, v);
+            } else if (f == 1) {
+                cpx a[16];
+                tmem_unpark(park0, a);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) a[q] = mk(a[q].x * (v[q].y * p.scale), a[q].y * (v[q].x * p.scale));   // -u dvortdx
+                tmem_park(park0, a);
+            } else if (f == 2) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = mk(v[q].y * p.scale, v[q].x * p.scale);      // v
+                tmem_park(park1, v);
+            }
+        }
+        // J = (-u dvortdx) - v dvortdy, formed in place in v (two register sets live, not three)   main.cpp:225-227
+        {
+            cpx a[16];
+            tmem_unpark(park1, a);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = mk(a[q].x * (v[q].y * p.scale), a[q].y * (v[q].x * p.scale));      // v dvortdy
+            tmem_unpark(park0, a);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = mk(a[q].x - v[q].x, a[q].y - v[q].y);
+        }
+        if (p.real_in != nullptr) {
+            const float *sa = p.real_in + ro, *sb = sa + NY;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = mk(v[q].x + __ldg(sa + t + q * G), v[q].y + __ldg(sb + t + q * G));
+        }
+        r2c_pair<NY, false>(v, p.spec_out + po, p, alive ? p.pitch : 0, sm, t, tw, bar);
+    }
+#undef XFB_FETCH
+#undef XFB_PAIR_OF
+    tmem_free_cta<C::TCOLS>(tbase);
+}
+
 template <int NY, int MODE, bool DIST>
 __global__ void __launch_bounds__(PairCfg<NY>::THREADS, PairCfg<NY>::MINB)
 rowpair_kernel(const RowParams p)
