@@ -456,7 +456,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slab", action="store_true", help="one grid slab-decomposed over the ranks (default: one ensemble member per GPU)")
-    ap.add_argument("--chunks", type=int, default=4, help="--slab: chunks of the compute/exchange overlap")
+    ap.add_argument("--chunks", type=int, default=8, help="--slab: chunks of the compute/exchange overlap")
     ap.add_argument("--slab-check", type=int, default=0, help="--slab: first verify against the single-GPU path at this grid size")
     args = ap.parse_args()
     if args.grid is None:

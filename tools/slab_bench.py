@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--grid", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--chunks", type=int, default=4)
+    ap.add_argument("--chunks", type=int, default=8)
     ap.add_argument("--check", type=int, default=0)
     ap.add_argument("--field", default="const", choices=["const", "elliptic"])
     ap.add_argument("--e2e-steps", type=int, default=3)

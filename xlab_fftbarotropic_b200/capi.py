@@ -262,7 +262,7 @@ class Backend:
 class SlabBackend(Backend):
     """One rank of a slab-decomposed grid (one process per GPU, NCCL all-to-all).  Fields are the LOCAL rows."""
 
-    def __init__(self, n: int, rank: int, nranks: int, unique_id: bytes, nchunks: int = 4, lx: float = 600000.0,
+    def __init__(self, n: int, rank: int, nranks: int, unique_id: bytes, nchunks: int = 8, lx: float = 600000.0,
                  nu: float = 6.5, device: int = 0):
         self.nx, self.ny, self.hy, self.batch = n, n, n // 2 + 1, 1
         self.lx, self.ly, self.nu = lx, lx, nu
