@@ -129,10 +129,9 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
                     // plain forward transform of the tile into the tile-major state (xfb_set_vorticity: main.cpp:256)
 #pragma unroll
                     for (int k = 0; k < 16; ++k) p.z0[e0 + (size_t)(k * G) * srow] = v[0][k];
-                    continue;
                 }
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < (MODE == COL_FWDT ? 0 : 2); ++h) {
                     cpx z0v[8], zkv[8], av[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) z0v[q] = p.z0[e0 + (size_t)((8 * h + q) * G) * srow];
