@@ -150,7 +150,10 @@ def run_reference_steps(n: int, dt: float, steps_a: int, steps_b: int, threads: 
             t0 = time.perf_counter()
             subprocess.run([exe], cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
             times.append(time.perf_counter() - t0)
-    return (times[1] - times[0]) / (steps_b - steps_a), None
+    per_step = (times[1] - times[0]) / (steps_b - steps_a)
+    if per_step <= 0:          # tiny samples: start-up noise larger than the steps themselves; fall back to the long run alone
+        per_step = times[1] / steps_b
+    return per_step, None
 
 
 def cpu_baseline(sample_n: int, nsteps: int):
