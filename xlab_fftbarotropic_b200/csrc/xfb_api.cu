@@ -765,7 +765,7 @@ static int field_to_device(xfb_handle h, int member, int which, float *dout)
         return 0;
     }
     if ((which == XFB_TFIL || which == XFB_DEFORM) && fused_diag_ok(h))
-        return fused_diag(h, member, 0, which == XFB_TFIL ? dout : h->real_a, which == XFB_DEFORM ? dout : h->real_b);
+        return fused_diag(h, member, 0, which == XFB_TFIL ? dout : h->real_c, which == XFB_DEFORM ? dout : h->real_b);   // dout may be real_a
     if (which == XFB_TFIL || which == XFB_DEFORM) {
         if (psi_second(h, member, 0, h->real_b)) return XFB_E_CUDA;
         if (psi_second(h, member, 1, h->real_c)) return XFB_E_CUDA;
