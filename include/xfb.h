@@ -45,7 +45,8 @@ enum {
     XFB_TFIL = 5,        /* filamentation time   README.md:5 (Rozoff et al. 2006) */
     XFB_DEFORM = 6,      /* deformation factor   README.md:7 */
     XFB_DVORTDX = 7,     /* dvortdx_step_N.bin   src/main.cpp:156-162 (OUTPUT_GRAD_VORT) */
-    XFB_DVORTDY = 8      /* dvortdy_step_N.bin   src/main.cpp:170-176 */
+    XFB_DVORTDY = 8,     /* dvortdy_step_N.bin   src/main.cpp:170-176 */
+    XFB_TRACER = 9       /* passive tracer of xfb_set_tracer (no reference counterpart) */
 };
 
 /* tables of xfb_get_table (src/fftwfop.cpp:5-79) */
@@ -110,6 +111,16 @@ int xfb_get_diagnostics(xfb_handle h, int member, float *tfil, float *deform);
 /* effective-diffusivity histograms (README.md:6, Hendricks & Schubert 2009): per bin of the
  * tracer zeta in [cmin,cmax): area and integral of |grad zeta|^2 (float64[nbins] each, host) */
 int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cmax, double *area, double *grad2);
+
+/* ---- passive tracer (the reference has none) -------------------------
+ * dc/dt = -u c_x - v c_y + kappa lap(c), advanced by xfb_step together with the vorticity: every Runge-Kutta stage
+ * uses that stage's velocity, the tendency is dealiased and combined exactly like the vorticity's
+ * (src/main.cpp:225-251,286-312 with c for vort and kappa for NU), so a tracer equal to the vorticity with
+ * kappa == nu and no forcing stays bit-identical to it.  `tracer` is nx*ny floats, host or device; kappa is one value
+ * per handle (the last call's).  Fused single-GPU grids only (power of two, <= 8192); XFB_E_SIZE otherwise.
+ * Read back with xfb_get_field(..., XFB_TRACER, ...); effective-diffusivity histograms over the tracer: */
+int xfb_set_tracer(xfb_handle h, int member, const float *tracer, float kappa);
+int xfb_get_tracer_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cmax, double *area, double *grad2);
 
 /* ---- pressure inversion: replaces the loop body of src/invert_pres.cpp:132-187 ---------------*/
 int xfb_invert_pres(xfb_handle h, const float *psi, float *pres, size_t ref_x, size_t ref_y, float rho, float f);

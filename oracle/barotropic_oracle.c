@@ -35,6 +35,11 @@ typedef struct {
     float *vort, *u, *v, *dvortdx, *dvortdy, *dvortdt, *workspace, *vort_src;
     fftwf_complex *vort_c0, *vort_c, *lvort_c, *dvortdt_c, *tmp_c, *psi_c, *rk1_c, *rk2_c, *rk3_c, *rk4_c;
     fftwf_plan p_fwd, p_bwd;
+    /* passive tracer (no reference code, see orc_set_tracer) */
+    int has_tracer;
+    float kappa;
+    float *trc, *dtrcdx, *dtrcdy;
+    fftwf_complex *trc_c0, *trc_c, *ltrc_c, *dtrcdt_c, *trk1_c, *trk2_c, *trk3_c, *trk4_c;
 } orc_t;
 
 #define HIDX(o, i, j) ((size_t)(o)->hy * (size_t)(i) + (size_t)(j))
@@ -106,6 +111,12 @@ void orc_destroy(orc_t *o)
     fftwf_complex *c[] = {o->vort_c0, o->vort_c, o->lvort_c, o->dvortdt_c, o->tmp_c, o->psi_c,
                           o->rk1_c, o->rk2_c, o->rk3_c, o->rk4_c};
     for (size_t k = 0; k < sizeof(c) / sizeof(c[0]); ++k) fftwf_free(c[k]);
+    if (o->has_tracer) {
+        float *tr[] = {o->trc, o->dtrcdx, o->dtrcdy};
+        for (size_t k = 0; k < sizeof(tr) / sizeof(tr[0]); ++k) fftwf_free(tr[k]);
+        fftwf_complex *tc[] = {o->trc_c0, o->trc_c, o->ltrc_c, o->dtrcdt_c, o->trk1_c, o->trk2_c, o->trk3_c, o->trk4_c};
+        for (size_t k = 0; k < sizeof(tc) / sizeof(tc[0]); ++k) fftwf_free(tc[k]);
+    }
     fftwf_destroy_plan(o->p_fwd); fftwf_destroy_plan(o->p_bwd);
     free(o);
 }
@@ -206,6 +217,64 @@ static void get_dvortdt(orc_t *o, int want_psi)
     }
 }
 
+/* Passive tracer c advected by the flow of the SAME Runge-Kutta stage (for effective-
+ * diffusivity diagnostics on a tracer other than the vorticity, Hendricks & Schubert 2009):
+ *     dc/dt = -u c_x - v c_y + kappa lap(c)
+ * The reference has no tracer: PARITY UNPINNED.  The restatement mirrors the vorticity tendency operation for
+ * operation (main.cpp:151-168 for the gradients, :225-227 for the product, :237-243 for the transform and the
+ * diffusion term) so that c == vort with kappa == nu and no source reproduces the vorticity exactly.
+ * Must run right after get_dvortdt: o->u, o->v hold the stage's velocity. */
+static void get_dtrcdt(orc_t *o)
+{
+    const int grids = (int)o->grids, hgrids = (int)o->hgrids;
+    orc_laplacian(o, o->trc_c, o->ltrc_c);
+    orc_gradx(o, o->trc_c, o->tmp_c);
+    orc_c2r(o, o->tmp_c, o->dtrcdx); backward_normalize(o, o->dtrcdx);
+    orc_grady(o, o->trc_c, o->tmp_c);
+    orc_c2r(o, o->tmp_c, o->dtrcdy); backward_normalize(o, o->dtrcdy);
+    for (int i = 0; i < grids; ++i) o->dvortdt[i] = -o->u[i] * o->dtrcdx[i] - o->v[i] * o->dtrcdy[i];
+    orc_r2c(o, o->dvortdt, o->dtrcdt_c);
+    for (int i = 0; i < hgrids; ++i) {
+        o->dtrcdt_c[i][0] += o->ltrc_c[i][0] * o->kappa;
+        o->dtrcdt_c[i][1] += o->ltrc_c[i][1] * o->kappa;
+    }
+}
+
+static void evolve_tracer(orc_t *o, fftwf_complex *rk, float dt)
+{
+    const int hgrids = (int)o->hgrids;
+    for (int i = 0; i < hgrids; ++i) {
+        o->trc_c[i][0] = o->trc_c0[i][0] + rk[i][0] * dt;
+        o->trc_c[i][1] = o->trc_c0[i][1] + rk[i][1] * dt;
+    }
+}
+
+/* physical tracer field + diffusivity; allocates the tracer state on first use */
+void orc_set_tracer(orc_t *o, const float *c, float kappa)
+{
+    if (!o->has_tracer) {
+        float **r[] = {&o->trc, &o->dtrcdx, &o->dtrcdy};
+        for (size_t k = 0; k < sizeof(r) / sizeof(r[0]); ++k) *r[k] = (float *)fftwf_malloc(sizeof(float) * o->grids);
+        fftwf_complex **cc[] = {&o->trc_c0, &o->trc_c, &o->ltrc_c, &o->dtrcdt_c, &o->trk1_c, &o->trk2_c, &o->trk3_c, &o->trk4_c};
+        for (size_t k = 0; k < sizeof(cc) / sizeof(cc[0]); ++k) {
+            *cc[k] = (fftwf_complex *)fftwf_malloc(sizeof(fftwf_complex) * o->hgrids);
+            memset(*cc[k], 0, sizeof(fftwf_complex) * o->hgrids);
+        }
+        o->has_tracer = 1;
+    }
+    o->kappa = kappa;
+    memcpy(o->trc, c, sizeof(float) * o->grids);
+    orc_r2c(o, o->trc, o->trc_c);
+}
+
+/* current tracer in physical space */
+void orc_get_tracer(orc_t *o, float *out)
+{
+    memcpy(o->tmp_c, o->trc_c, sizeof(fftwf_complex) * o->hgrids);      /* c2r destroys its input */
+    orc_c2r(o, o->tmp_c, o->trc); backward_normalize(o, o->trc);
+    memcpy(out, o->trc, sizeof(float) * o->grids);
+}
+
 /* main.cpp:246-251 */
 static void evolve(orc_t *o, fftwf_complex *rk, float dt)
 {
@@ -239,8 +308,25 @@ void orc_step(orc_t *o, int nsteps, float dt)
     const int hgrids = (int)o->hgrids;
     for (int s = 0; s < nsteps; ++s) {
         memcpy(o->vort_c0, o->vort_c, sizeof(fftwf_complex) * o->hgrids);          /* :286 */
+        if (o->has_tracer) memcpy(o->trc_c0, o->trc_c, sizeof(fftwf_complex) * o->hgrids);
         for (int k = 0; k < 4; ++k) {
             get_dvortdt(o, 0);                                                     /* :290 */
+            if (o->has_tracer) {
+                /* same stage, same velocity; same dealias / evolve / final-combine expressions as below */
+                get_dtrcdt(o);
+                switch (k) {
+                case 0: orc_dealias(o, o->dtrcdt_c, o->trk1_c); evolve_tracer(o, o->trk1_c, dt / 2.0f); break;
+                case 1: orc_dealias(o, o->dtrcdt_c, o->trk2_c); evolve_tracer(o, o->trk2_c, dt / 2.0f); break;
+                case 2: orc_dealias(o, o->dtrcdt_c, o->trk3_c); evolve_tracer(o, o->trk3_c, dt); break;
+                case 3:
+                    orc_dealias(o, o->dtrcdt_c, o->trk4_c);
+                    for (int i = 0; i < hgrids; ++i) {
+                        o->trc_c[i][0] = o->trc_c0[i][0] + (o->trk1_c[i][0] + 2.0f * o->trk2_c[i][0] + 2.0f * o->trk3_c[i][0] + o->trk4_c[i][0]) * dt / 6.0f;
+                        o->trc_c[i][1] = o->trc_c0[i][1] + (o->trk1_c[i][1] + 2.0f * o->trk2_c[i][1] + 2.0f * o->trk3_c[i][1] + o->trk4_c[i][1]) * dt / 6.0f;
+                    }
+                    break;
+                }
+            }
             switch (k) {
             case 0: orc_dealias(o, o->dvortdt_c, o->rk1_c); evolve(o, o->rk1_c, dt / 2.0f); break; /* :296 */
             case 1: orc_dealias(o, o->dvortdt_c, o->rk2_c); evolve(o, o->rk2_c, dt / 2.0f); break; /* :299 */
@@ -351,14 +437,15 @@ void orc_diagnostics(orc_t *o, float *tfil, float *deform, float *s1_out, float 
  *   area[b] += dx dy ;  grad2[b] += |grad c|^2 dx dy       (float64 accumulators)
  * |grad c|^2 from the spectral derivatives the tendency already forms (main.cpp:151-168).
  */
-void orc_keff_hist(orc_t *o, int nbins, float cmin, float cmax, double *area, double *grad2)
+static void keff_hist_of(orc_t *o, fftwf_complex *c_c, int nbins, float cmin, float cmax, double *area, double *grad2)
 {
     const int grids = (int)o->grids;
     const double da = ((double)o->lx / o->n) * ((double)o->ly / o->n);
-    orc_c2r(o, o->vort_c, o->vort); backward_normalize(o, o->vort);
-    orc_gradx(o, o->vort_c, o->tmp_c);
+    memcpy(o->psi_c, c_c, sizeof(fftwf_complex) * o->hgrids);           /* c2r destroys its input */
+    orc_c2r(o, o->psi_c, o->vort); backward_normalize(o, o->vort);
+    orc_gradx(o, c_c, o->tmp_c);
     orc_c2r(o, o->tmp_c, o->dvortdx); backward_normalize(o, o->dvortdx);
-    orc_grady(o, o->vort_c, o->tmp_c);
+    orc_grady(o, c_c, o->tmp_c);
     orc_c2r(o, o->tmp_c, o->dvortdy); backward_normalize(o, o->dvortdy);
     for (int b = 0; b < nbins; ++b) { area[b] = 0; grad2[b] = 0; }
     const float scale = (float)nbins / (cmax - cmin);
@@ -370,6 +457,17 @@ void orc_keff_hist(orc_t *o, int nbins, float cmin, float cmax, double *area, do
         area[b] += da;
         grad2[b] += (double)g2 * da;
     }
+}
+
+void orc_keff_hist(orc_t *o, int nbins, float cmin, float cmax, double *area, double *grad2)
+{
+    keff_hist_of(o, o->vort_c, nbins, cmin, cmax, area, grad2);
+}
+
+/* the same histograms over the passive tracer */
+void orc_tracer_keff_hist(orc_t *o, int nbins, float cmin, float cmax, double *area, double *grad2)
+{
+    keff_hist_of(o, o->trc_c, nbins, cmin, cmax, area, grad2);
 }
 
 /* kappa_eff(C_b) on the bin edges C_b = cmin + b (cmax-cmin)/nbins, b = 1..nbins-1:

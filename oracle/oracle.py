@@ -47,6 +47,9 @@ def lib():
         L.orc_invert_pres.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_float, C.c_float]
         L.orc_diagnostics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_keff_hist.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        L.orc_tracer_keff_hist.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        L.orc_set_tracer.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+        L.orc_get_tracer.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_keff_from_hist.argtypes = [C.c_int, C.c_float, C.c_float, C.c_double, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
         L.xfb_shim_set_threads.argtypes = [C.c_int]
@@ -156,6 +159,23 @@ class Oracle:
         area = np.zeros(nbins, np.float64)
         g2 = np.zeros(nbins, np.float64)
         lib().orc_keff_hist(self._o, nbins, cmin, cmax, _p(area), _p(g2))
+        return area, g2
+
+    # passive tracer (no reference code: a restatement of dc/dt = -u.grad c + kappa lap c in the
+    # vorticity tendency's own operation order, see barotropic_oracle.c get_dtrcdt)
+    def set_tracer(self, c, kappa: float):
+        c = np.ascontiguousarray(c, dtype=np.float32).reshape(self.n, self.n)
+        lib().orc_set_tracer(self._o, _p(c), float(kappa))
+
+    def get_tracer(self):
+        out = np.empty((self.n, self.n), np.float32)
+        lib().orc_get_tracer(self._o, _p(out))
+        return out
+
+    def tracer_keff_hist(self, nbins: int, cmin: float, cmax: float):
+        area = np.zeros(nbins, np.float64)
+        g2 = np.zeros(nbins, np.float64)
+        lib().orc_tracer_keff_hist(self._o, nbins, cmin, cmax, _p(area), _p(g2))
         return area, g2
 
 

@@ -13,13 +13,14 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("XFB_LIB") or os.path.join(HERE, "libxfb.so")   # XFB_LIB: A/B builds of the same ABI
 
-VORT, PSI, U, V, SRC, TFIL, DEFORM, DVORTDX, DVORTDY = range(9)
+VORT, PSI, U, V, SRC, TFIL, DEFORM, DVORTDX, DVORTDY, TRACER = range(10)
 TAB_GRADX, TAB_GRADY, TAB_LAP, TAB_LAPINV, TAB_MASK = range(5)
 
 SYMBOLS = [
     "xfb_last_error", "xfb_create", "xfb_destroy", "xfb_sync", "xfb_gradx", "xfb_grady", "xfb_laplacian",
     "xfb_invert_laplacian", "xfb_dealias", "xfb_get_table", "xfb_r2c", "xfb_c2r", "xfb_set_vorticity",
     "xfb_set_spectrum", "xfb_get_spectrum", "xfb_set_source", "xfb_step", "xfb_get_field", "xfb_get_keff_hist", "xfb_get_diagnostics",
+    "xfb_set_tracer", "xfb_get_tracer_keff_hist",
     "xfb_host_alloc", "xfb_host_free", "xfb_get_field_async", "xfb_wait_field",
     "xfb_invert_pres", "xfb_launch_count", "xfb_stream", "xfb_size_supported", "xfb_profile", "xfb_profile_read",
     "xfb_slab_partition", "xfb_nccl_unique_id", "xfb_create_dist", "xfb_profile_read_a2a", "xfb_slab_transport",
@@ -62,6 +63,8 @@ def load():
     L.xfb_get_field_async.argtypes = [vp, ci, ci, vp, C.POINTER(ci)]
     L.xfb_wait_field.argtypes = [vp, ci]
     L.xfb_get_keff_hist.argtypes = [vp, ci, ci, cf, cf, vp, vp]
+    L.xfb_get_tracer_keff_hist.argtypes = [vp, ci, ci, cf, cf, vp, vp]
+    L.xfb_set_tracer.argtypes = [vp, ci, vp, cf]
     L.xfb_invert_pres.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, cf, cf]
     L.xfb_launch_count.restype = C.c_longlong
     L.xfb_launch_count.argtypes = [vp]
@@ -232,6 +235,17 @@ class Backend:
         area = np.zeros(nbins, np.float64)
         g2 = np.zeros(nbins, np.float64)
         self._ck(self._L.xfb_get_keff_hist(self._h, member, nbins, cmin, cmax, _ptr(area), _ptr(g2)))
+        return area, g2
+
+    # passive tracer: advected by xfb_step with the flow of each stage; read back with get_field(TRACER)
+    def set_tracer(self, c, kappa, member=0):
+        c = np.ascontiguousarray(c, dtype=np.float32).reshape(self.nx, self.ny)
+        self._ck(self._L.xfb_set_tracer(self._h, member, _ptr(c), float(kappa)))
+
+    def tracer_keff_hist(self, nbins, cmin, cmax, member=0):
+        area = np.zeros(nbins, np.float64)
+        g2 = np.zeros(nbins, np.float64)
+        self._ck(self._L.xfb_get_tracer_keff_hist(self._h, member, nbins, cmin, cmax, _ptr(area), _ptr(g2)))
         return area, g2
 
     def invert_pres(self, psi, ref_x=0, ref_y=0, rho=1.0, f=1e-5):

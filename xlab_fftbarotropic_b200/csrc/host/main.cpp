@@ -8,7 +8,8 @@
 // Compile-time constants of src/configuration.hpp:13-36 are run-time options with the same defaults:
 //   -n <NPTS=768> -d <dt=3> -t <total_steps=1200> -r <record_step=100> -L <600000> -N <NU=6.5>
 // Additions: -g <cuda device>, -D (also write filamentation time / deformation factor at record steps),
-//   -q (no per-step line).
+//   -q (no per-step line), -c <tracer file> [-k <kappa>] (advect a passive tracer read from <input dir>, written as
+//   tracer_step_N.bin after the reference's five files; power-of-two grids only).
 // Record output is asynchronous: at a record step the five fields are formed on the GPU and copied
 // to pinned host buffers on a second stream (xfb_get_field_async) while the next stretch of steps already runs; a
 // writer thread waits for each buffer, calls writeField and appends the `log` line -- same files, same order as the
@@ -44,14 +45,15 @@ using namespace VORT_SRC_READER;
 int main(int argc, char *args[])
 {
     std::string input = "input", output = "output", init_file = "initial_vorticity.bin";   // configuration.hpp:39-41
-    std::string vort_src_filename;
+    std::string vort_src_filename, tracer_file;
+    float kappa = -1.0f;
     RECIPE_TYPE recipe_type = EMPTY;
     int npts = 768, record_step = 100, total_steps = -1, device = 0;
     float L = 600000.0f, NU = 6.5f, dt = 3.0f;
     bool diagnostics = false, quiet = false;
 
     int opt;
-    while ((opt = getopt(argc, args, "I:O:o:i:s:f:n:d:t:r:L:N:g:Dq")) != EOF) {
+    while ((opt = getopt(argc, args, "I:O:o:i:s:f:n:d:t:r:L:N:g:c:k:Dq")) != EOF) {
         switch (opt) {
         case 'I': input = optarg; break;
         case 'O': case 'o': output = optarg; break;
@@ -65,6 +67,8 @@ int main(int argc, char *args[])
         case 'L': L = (float)std::atof(optarg); break;
         case 'N': NU = (float)std::atof(optarg); break;
         case 'g': device = std::atoi(optarg); break;
+        case 'c': tracer_file = optarg; break;        // passive tracer: initial field <input>/<file>, tracer_step_N.bin
+        case 'k': kappa = (float)std::atof(optarg); break;   // its diffusivity (default: NU)
         case 'D': diagnostics = true; break;
         case 'q': quiet = true; break;
         }
@@ -105,6 +109,16 @@ int main(int argc, char *args[])
     std::printf("Initialization complete.\n");
     CHECK(xfb_set_vorticity(h, 0, field.data()));                  // step 01, main.cpp:256
 
+    const bool tracer = !tracer_file.empty();
+    if (tracer) {
+        std::snprintf(filename, sizeof(filename), "%s/%s", input.c_str(), tracer_file.c_str());
+        if (readFieldChecked(filename, field.data(), GRIDS) != 0) {
+            std::fprintf(stderr, "main.out: cannot read the tracer field %s\n", filename);
+            return 1;
+        }
+        CHECK(xfb_set_tracer(h, 0, field.data(), kappa >= 0.0f ? kappa : NU));
+    }
+
     // ---- asynchronous record output: one pinned buffer per field kind, a writer thread, jobs in log order
     struct Job { int ticket; float *buf; std::string file; };
     std::deque<Job> jobs;
@@ -136,7 +150,7 @@ int main(int argc, char *args[])
         std::unique_lock<std::mutex> lk(mu);
         cv_idle.wait(lk, [&] { return pending == 0; });
     };
-    const int NKIND = 7;
+    const int NKIND = 8;
     float *pinned[NKIND] = {nullptr};
     auto record = [&](int kind, const char *stem, int which, int step) -> int {
         if (!pinned[kind] && xfb_host_alloc(&pinned[kind], GRIDS) != 0) return 1;
@@ -173,7 +187,8 @@ int main(int argc, char *args[])
             // same order as the reference's log: source, vort (main.cpp:268-278), then psi, u, v (:183-222)
             if (record(0, "vort_src_input", XFB_SRC, step) || record(1, "vort", XFB_VORT, step) ||
                 record(2, "psi", XFB_PSI, step) || record(3, "u", XFB_U, step) || record(4, "v", XFB_V, step) ||
-                (diagnostics && (record(5, "tfil", XFB_TFIL, step) || record(6, "deform", XFB_DEFORM, step)))) {
+                (diagnostics && (record(5, "tfil", XFB_TFIL, step) || record(6, "deform", XFB_DEFORM, step))) ||
+                (tracer && record(7, "tracer", XFB_TRACER, step))) {
                 std::fprintf(stderr, "main.out: %s\n", xfb_last_error());
                 shutdown_writer();
                 return 1;

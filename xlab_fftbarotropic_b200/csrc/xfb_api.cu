@@ -309,7 +309,7 @@ int xfb::destroy_impl(xfb_handle h)
         cudaStreamDestroy(h->rec_stream);
     }
     void *ptrs[] = {h->tw, h->kx, h->ky, h->kx2, h->ky2, h->z0, h->zk, h->acc, h->jint, h->t_block, h->src, h->dg, h->real_a,
-                    h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b, h->recv_block, h->sync_buf};
+                    h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b, h->recv_block, h->sync_buf, h->c0, h->ck, h->cacc, h->cjint, h->tc[0]};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto pool : {h->ev_row, h->ev_col, h->ev_a2a})
@@ -530,13 +530,27 @@ extern "C" int xfb_c2r(xfb_handle h, const float *spec_in, float *real_out)
 // stepper tier
 // ------------------------------------------------------------------------------------------------
 static bool fused_diag_ok(xfb_handle h);
-static int fused_products(xfb_handle h, int member, int kind, int nfields);
-static int fused_diag(xfb_handle h, int member, int kind, float *out0, float *out1);
+static int fused_products(xfb_handle h, int member, int kind, int nfields, const cpx *state = nullptr);
+static int fused_diag(xfb_handle h, int member, int kind, float *out0, float *out1, const cpx *state = nullptr);
 
 static int check_member(xfb_handle h, int member)
 {
     if (!h) return fail(XFB_E_ARG, "null handle");
     if (member < 0 || member >= h->batch) return fail(XFB_E_ARG, "member %d out of range [0,%d)", member, h->batch);
+    return 0;
+}
+
+// physical field (device) -> tile-major spectral state array of one member: y pass (pair kernel) then the TMA-staged
+// x pass straight into the state (main.cpp:256)
+static int fused_forward_to_state(xfb_handle h, const float *din, cpx *state_member)
+{
+    RowParams r; fill_row(h, r, h->nx);
+    r.real_in = din; r.spec_out = h->spec_a;
+    CKL(h, launch_row(h->ny, ROW_R2C, r, h->stream));
+    ColParams c; fill_col(h, c);
+    c.jint = h->spec_a; c.z0 = state_member; c.zk = c.z0; c.acc = c.z0;
+    c.st_tile_stride = (long long)h->nx * h->tw_state; c.st_row_stride = h->tw_state;
+    CKL(h, launch_col(h->nx, COL_FWDT, c, 1, h->stream));
     return 0;
 }
 
@@ -549,14 +563,7 @@ extern "C" int xfb_set_vorticity(xfb_handle h, int member, const float *vort)
     const void *din;
     if (stage_in(h, vort, h->real_a, sizeof(float) * h->grids, &din)) return XFB_E_CUDA;
     if (fused_diag_ok(h)) {
-        // y pass (pair kernel) then the TMA-staged x pass straight into the tile-major state
-        RowParams r; fill_row(h, r, h->nx);
-        r.real_in = (const float *)din; r.spec_out = h->spec_a;
-        CKL(h, launch_row(h->ny, ROW_R2C, r, h->stream));
-        ColParams c; fill_col(h, c);
-        c.jint = h->spec_a; c.z0 = h->z0 + (size_t)member * h->hpad; c.zk = c.z0; c.acc = c.z0;
-        c.st_tile_stride = (long long)h->nx * h->tw_state; c.st_row_stride = h->tw_state;
-        CKL(h, launch_col(h->nx, COL_FWDT, c, 1, h->stream));
+        if (fused_forward_to_state(h, (const float *)din, h->z0 + (size_t)member * h->hpad)) return XFB_E_CUDA;
     } else {
         if (fwd2d(h, (const float *)din, h->spec_a, h->spec_b)) return XFB_E_CUDA;
         if (launch_pw(h, OP_COPY, h->spec_b, h->pitch, h->z0 + (size_t)member * h->hpad, h->pitch, h->pitch, 0, h->tw_state))
@@ -618,6 +625,43 @@ extern "C" int xfb_set_source(xfb_handle h, int member, const float *src)
     return 0;
 }
 
+// Passive tracer: dc/dt = -u c_x - v c_y + kappa lap(c), advanced inside xfb_step by the
+// velocity of the same Runge-Kutta stage with the vorticity equation's own operation order (dealiased tendency, same
+// evolve / final combine).  The reference has no tracer; the definition is the oracle's (barotropic_oracle.c
+// get_dtrcdt).  Per stage it costs one more K-ROW launch (the Jacobian kernel on T_u, T_cx, T_v, T_cy -- u and v are
+// read from the vorticity stage's product arrays) and one K-COL launch (COL_TSTEP: 2 products instead of 4).
+extern "C" int xfb_set_tracer(xfb_handle h, int member, const float *tracer, float kappa)
+{
+    if (check_member(h, member)) return XFB_E_ARG;
+    if (!tracer) return fail(XFB_E_ARG, "null tracer");
+    if (!fused_diag_ok(h))
+        return fail(XFB_E_SIZE, "the passive tracer runs on the fused single-GPU kernels only (power-of-two grids <= 8192, no slab)");
+    CK(cudaSetDevice(h->device));
+    const size_t sb = sizeof(cpx) * h->hpad * h->batch;
+    if (!h->c0) {
+        cpx **state[] = {&h->c0, &h->ck, &h->cacc, &h->cjint};
+        for (auto pp : state) {
+            if (dev_alloc((void **)pp, sb)) return XFB_E_CUDA;
+            CK(cudaMemsetAsync(*pp, 0, sb, h->stream));
+        }
+        if (dev_alloc((void **)&h->tc[0], 2 * sb)) return XFB_E_CUDA;
+        CK(cudaMemsetAsync(h->tc[0], 0, 2 * sb, h->stream));
+        h->tc[1] = h->tc[0] + h->hpad * h->batch;
+    }
+    const void *din;
+    if (stage_in(h, tracer, h->real_a, sizeof(float) * h->grids, &din)) return XFB_E_CUDA;
+    if (fused_forward_to_state(h, (const float *)din, h->c0 + (size_t)member * h->hpad)) return XFB_E_CUDA;
+    if (!h->has_tracer || h->kappa != kappa) {
+        // the captured step has no tracer launches / another diffusivity baked in
+        if (h->step_graph) { cudaGraphExecDestroy((cudaGraphExec_t)h->step_graph); h->step_graph = nullptr; }
+    }
+    h->has_tracer = true;
+    h->kappa = kappa;
+    h->tcf_valid = false;
+    if (!is_device_ptr(tracer)) CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 extern "C" int xfb_step(xfb_handle h, int nsteps, float dt)
 {
     if (!h) return fail(XFB_E_ARG, "null handle");
@@ -639,10 +683,26 @@ extern "C" int xfb_step(xfb_handle h, int nsteps, float dt)
         CKL(h, launch_col(h->nx, COL_PRO, c, h->batch, h->stream));
         h->tf_valid = true;
     }
+    // passive tracer: its own state and Jacobian arrays, the vorticity stage's velocity products
+    const bool tracer = h->has_tracer;
+    ColParams ct = c;
+    RowParams rt = r;
+    if (tracer) {
+        ct.jint = h->cjint; ct.z0 = h->c0; ct.zk = h->ck; ct.acc = h->cacc; ct.nu = h->kappa;
+        ct.t_out[0] = h->tc[0]; ct.t_out[1] = h->tc[1]; ct.t_out[2] = h->tc[0]; ct.t_out[3] = h->tc[1];
+        rt.spec_in[0] = h->tc[0]; rt.spec_in[1] = h->tc[1];           // c_x, c_y ; [2], [3] stay u, v
+        rt.real_in = nullptr; rt.spec_out = h->cjint;
+        if (nsteps > 0 && !h->tcf_valid) {
+            CKL(h, launch_col(h->nx, COL_TPRO, ct, h->batch, h->stream));
+            h->tcf_valid = true;
+        }
+    }
+    const int launches_per_step = tracer ? 16 : 8;
     auto one_step = [&]() -> int {
         for (int k = 1; k <= 4; ++k) {
             if (h->profiling) cudaEventRecord(next_event(h->ev_row, h->ev_row_used), h->stream);
             CKL(h, launch_row(h->ny, ROW_JAC, r, h->stream));
+            if (tracer) CKL(h, launch_row(h->ny, ROW_JAC, rt, h->stream));     // before K-COL overwrites u, v
             if (h->profiling) {
                 cudaEventRecord(next_event(h->ev_row, h->ev_row_used), h->stream);
                 cudaEventRecord(next_event(h->ev_col, h->ev_col_used), h->stream);
@@ -650,6 +710,10 @@ extern "C" int xfb_step(xfb_handle h, int nsteps, float dt)
             c.stage = k;
             c.dt_stage = (k == 3) ? dt : dt / 2.0f;          // main.cpp:296,299,302
             CKL(h, launch_col(h->nx, COL_STEP, c, h->batch, h->stream));
+            if (tracer) {
+                ct.stage = k; ct.dt_stage = c.dt_stage;
+                CKL(h, launch_col(h->nx, COL_TSTEP, ct, h->batch, h->stream));
+            }
             if (h->profiling) cudaEventRecord(next_event(h->ev_col, h->ev_col_used), h->stream);
         }
         return 0;
@@ -685,7 +749,7 @@ extern "C" int xfb_step(xfb_handle h, int nsteps, float dt)
         }
         for (; s < nsteps; ++s) {
             CK(cudaGraphLaunch((cudaGraphExec_t)h->step_graph, h->stream));
-            h->launches += 8;
+            h->launches += launches_per_step;
         }
     }
     return 0;
@@ -697,10 +761,12 @@ static int derived_field(xfb_handle h, int member, int which, float *dout)
     const cpx *z = h->z0 + (size_t)member * h->hpad;
     const float scale = 1.0f / (float)((double)h->nx * (double)h->ny);
     const int P = h->pitch, T = h->tw_state;
+    if (which == XFB_TRACER && !h->has_tracer) return fail(XFB_E_STATE, "XFB_TRACER before xfb_set_tracer");
     if (fused_diag_ok(h)) {
         // record fields on the stepper's kernels: one K-COL launch (spectral multiplier + x pass, TMA-staged) and one
         // K-ROW launch (y pass, normalisation, sign); multipliers in float32 (<= 2 ulp from the operator tier's tables)
-        if (fused_products(h, member, 2 + which, 1)) return XFB_E_CUDA;
+        if (which == XFB_TRACER ? fused_products(h, member, 2 + XFB_VORT, 1, h->c0) : fused_products(h, member, 2 + which, 1))
+            return XFB_E_CUDA;
         RowParams r; fill_row(h, r, h->nx);
         r.spec_in[0] = h->dg; r.real_out = dout; r.scale = scale; r.negate = (which == XFB_U) ? 1 : 0;
         CKL(h, launch_row(h->ny, ROW_C2R, r, h->stream));
@@ -860,14 +926,14 @@ static bool fused_diag_ok(xfb_handle h)
 }
 
 // K-COL half: `nfields` spectral products of member's state, x-inverse-transformed into h->dg[0 .. nfields-1]
-static int fused_products(xfb_handle h, int member, int kind, int nfields)
+static int fused_products(xfb_handle h, int member, int kind, int nfields, const cpx *state)
 {
     if (!h->dg) {
         if (dev_alloc((void **)&h->dg, 3 * sizeof(cpx) * h->hpad)) return XFB_E_CUDA;
         CK(cudaMemsetAsync(h->dg, 0, 3 * sizeof(cpx) * h->hpad, h->stream));
     }
     ColParams c; fill_col(h, c);
-    c.z0 = h->z0 + (size_t)member * h->hpad; c.zk = c.z0; c.acc = c.z0; c.jint = h->jint;
+    c.z0 = const_cast<cpx *>(state ? state : h->z0) + (size_t)member * h->hpad; c.zk = c.z0; c.acc = c.z0; c.jint = h->jint;
     c.st_tile_stride = (long long)h->nx * h->tw_state; c.st_row_stride = h->tw_state;
     for (int f = 0; f < 4; ++f) c.t_out[f] = h->dg + (size_t)(f < 3 ? f : 2) * h->hpad;
     c.stage = kind;
@@ -876,9 +942,9 @@ static int fused_products(xfb_handle h, int member, int kind, int nfields)
     return 0;
 }
 
-static int fused_diag(xfb_handle h, int member, int kind, float *out0, float *out1)
+static int fused_diag(xfb_handle h, int member, int kind, float *out0, float *out1, const cpx *state)
 {
-    if (fused_products(h, member, kind, 3)) return XFB_E_CUDA;
+    if (fused_products(h, member, kind, 3, state)) return XFB_E_CUDA;
     RowParams r; fill_row(h, r, h->nx);
     for (int f = 0; f < 3; ++f) r.spec_in[f] = h->dg + (size_t)f * h->hpad;
     r.real_out = out0; r.real_out2 = out1; r.diag_kind = kind;
@@ -964,16 +1030,14 @@ __global__ void keff_hist_kernel(const float *c, const float *gx, const float *g
     }
 }
 
-extern "C" int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cmax, double *area, double *grad2)
+static int keff_hist_impl(xfb_handle h, int member, int nbins, float cmin, float cmax, double *area, double *grad2,
+                          const cpx *state)
 {
-    if (check_member(h, member)) return XFB_E_ARG;
     if (!area || !grad2 || nbins < 1 || nbins > 2048 || !(cmax > cmin)) return fail(XFB_E_ARG, "bad histogram arguments");
-    if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_keff_hist before xfb_set_vorticity");
-    NO_SLAB(h, "xfb_get_keff_hist");
     CK(cudaSetDevice(h->device));
     const bool fused = fused_diag_ok(h);
     if (fused) {
-        if (fused_diag(h, member, 1, h->real_a, h->real_b)) return XFB_E_CUDA;       // zeta, |grad zeta|^2
+        if (fused_diag(h, member, 1, h->real_a, h->real_b, state)) return XFB_E_CUDA;       // c, |grad c|^2
     } else {
         if (derived_field(h, member, XFB_VORT, h->real_a)) return XFB_E_CUDA;
         if (derived_field(h, member, XFB_DVORTDX, h->real_b)) return XFB_E_CUDA;
@@ -993,6 +1057,23 @@ extern "C" int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin
     memcpy(area, host.data(), sizeof(double) * nbins);
     memcpy(grad2, host.data() + nbins, sizeof(double) * nbins);
     return 0;
+}
+
+extern "C" int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cmax, double *area, double *grad2)
+{
+    if (check_member(h, member)) return XFB_E_ARG;
+    if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_keff_hist before xfb_set_vorticity");
+    NO_SLAB(h, "xfb_get_keff_hist");
+    return keff_hist_impl(h, member, nbins, cmin, cmax, area, grad2, nullptr);
+}
+
+// the same histograms over the passive tracer (Hendricks & Schubert 2009 use a tracer distinct from the vorticity)
+extern "C" int xfb_get_tracer_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cmax, double *area,
+                                        double *grad2)
+{
+    if (check_member(h, member)) return XFB_E_ARG;
+    if (!h->has_tracer) return fail(XFB_E_STATE, "xfb_get_tracer_keff_hist before xfb_set_tracer");
+    return keff_hist_impl(h, member, nbins, cmin, cmax, area, grad2, h->c0);
 }
 
 // ------------------------------------------------------------------------------------------------

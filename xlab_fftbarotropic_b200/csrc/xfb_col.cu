@@ -75,12 +75,12 @@ static int launch_colt_t(const ColParams &p, int batch, cudaStream_t st)
     }
     ColTMaps maps;
     const long long rows = (long long)NX * batch;
-    if (MODE == COL_STEP || MODE == COL_FWDT) {
+    if (MODE == COL_STEP || MODE == COL_FWDT || MODE == COL_TSTEP) {
         if (int e = make_pair_map(&maps.jint, p.jint, rows, p.pitch, C::TW, C::BOXR)) return e;
     } else {
         maps.jint = CUtensorMap();
     }
-    const int nout = (MODE == COL_FWDT) ? 0 : (MODE == COL_DIAG) ? p.nfields : 4;
+    const int nout = (MODE == COL_FWDT) ? 0 : (MODE == COL_DIAG) ? p.nfields : (MODE == COL_TSTEP || MODE == COL_TPRO) ? 2 : 4;
     for (int f = 0; f < 4; ++f) {
         if (f < nout) {
             if (int e = make_pair_map(&maps.t[f], p.t_out[f], rows, p.pitch, C::TW, C::BOXR)) return e;
@@ -135,6 +135,8 @@ static int launch_colt_n(int mode, const ColParams &p, int batch, cudaStream_t s
     }
     if (mode == COL_DIAG) return launch_colt_t<NX, COL_DIAG>(p, batch, st);
     if (mode == COL_FWDT) return launch_colt_t<NX, COL_FWDT>(p, batch, st);
+    if (mode == COL_TSTEP) return launch_colt_t<NX, COL_TSTEP>(p, batch, st);
+    if (mode == COL_TPRO) return launch_colt_t<NX, COL_TPRO>(p, batch, st);
     return mode == COL_STEP ? launch_colt_t<NX, COL_STEP>(p, batch, st) : launch_colt_t<NX, COL_PRO>(p, batch, st);
 }
 
@@ -169,8 +171,9 @@ int launch_col(int nx, int mode, const ColParams &p, int batch, cudaStream_t st)
 {
     // the stepper's modes run on the TMA-staged persistent kernel (XFB_COL_GEN1=1: first-generation kernel, A/B knob)
     static const bool gen1 = env_int("XFB_COL_GEN1", 0) != 0;
-    if ((mode == COL_DIAG || mode == COL_FWDT) && (gen1 || nx > 8192)) return (int)cudaErrorNotSupported;
-    if ((mode == COL_STEP || mode == COL_PRO || mode == COL_DIAG || mode == COL_FWDT) && !gen1) {
+    const bool colt_only = (mode == COL_DIAG || mode == COL_FWDT || mode == COL_TSTEP || mode == COL_TPRO);
+    if (colt_only && (gen1 || nx > 8192)) return (int)cudaErrorNotSupported;
+    if ((mode == COL_STEP || mode == COL_PRO || colt_only) && !gen1) {
         switch (nx) {
         case 256: return launch_colt_n<256>(mode, p, batch, st);
         case 512: return launch_colt_n<512>(mode, p, batch, st);

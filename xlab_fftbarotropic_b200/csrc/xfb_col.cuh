@@ -16,7 +16,9 @@
 
 namespace xfb {
 
-enum { COL_FWD = 0, COL_INV = 1, COL_STEP = 2, COL_PRO = 3, COL_DIAG = 4, COL_FWDT = 5 };
+// COL_TSTEP / COL_TPRO: COL_STEP / COL_PRO of the passive tracer (xfb_set_tracer): same forward transform, RK epilogue
+// (diffusivity in p.nu) and state update, but only the two gradient products i kx C, i ky C leave for K-ROW.
+enum { COL_FWD = 0, COL_INV = 1, COL_STEP = 2, COL_PRO = 3, COL_DIAG = 4, COL_FWDT = 5, COL_TSTEP = 6, COL_TPRO = 7 };
 
 struct ColParams {
     const cpx *jint;      // FWD/STEP: y-transformed lines, pair layout (see xfb_row.cuh): (i, j) at ((i>>1)*pitch + j)*2 + (i&1)

@@ -47,11 +47,14 @@ struct ColTMaps {
     CUtensorMap t[4];
 };
 
-template <int NX, int MODE>
+template <int NX, int MODE_>
 __global__ void __launch_bounds__(ColTCfg<NX>::THREADS, ColTCfg<NX>::MINB)
 colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int tiles_per_member, const int tiles_total)
 {
     typedef ColTCfg<NX> C;
+    // the tracer modes are the stepper's modes with two products instead of four
+    constexpr bool TRACER = (MODE_ == COL_TSTEP || MODE_ == COL_TPRO);
+    constexpr int MODE = (MODE_ == COL_TSTEP) ? COL_STEP : (MODE_ == COL_TPRO) ? COL_PRO : MODE_;
     constexpr int G = C::G, TW = C::TW, FW = C::FW, NG = C::NG;
     constexpr bool KEEP = (NG == 1);
     extern __shared__ unsigned char smem_dyn[];
@@ -194,7 +197,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
 
         // ------------------------------------------------------------------ prologue of the next stage + 4 inverse
         const cpx *zsrc = (MODE == COL_PRO || MODE == COL_DIAG || p.stage == 4) ? p.z0 : p.zk;
-        const int NF = (MODE == COL_FWDT) ? 0 : (MODE == COL_DIAG) ? p.nfields : 4;
+        const int NF = (MODE == COL_FWDT) ? 0 : (MODE == COL_DIAG) ? p.nfields : TRACER ? 2 : 4;
         if (KEEP && (MODE == COL_PRO || MODE == COL_DIAG)) {
             const size_t e0 = moff + (size_t)tl * (size_t)p.st_tile_stride + (size_t)t[0] * srow + c[0];
 #pragma unroll

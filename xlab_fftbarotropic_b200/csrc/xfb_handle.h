@@ -65,6 +65,10 @@ struct xfb_handle_s {
     void *step_graph;    // cudaGraphExec_t of one RK4 step (8 launches), valid for graph_dt / graph_src
     float graph_dt;
     const void *graph_src;
+    // passive tracer (xfb_set_tracer), allocated on first use: state like z0/zk/acc/jint, two gradient product arrays
+    xfb::cpx *c0, *ck, *cacc, *cjint, *tc[2];
+    float kappa;
+    bool has_tracer, tcf_valid;     // tcf_valid: tc[0..1] hold the gradient products of the current c0
     void *generic;       // non-null: grid served by the generic mixed-radix path (xfb_generic.cu), reference layout everywhere
     // ---- slab decomposition (xfb_dist.cu); nranks == 1 otherwise ------------------------------------
     // rank r holds physical rows [r*rows, (r+1)*rows) and the spectral columns of panels r*nchunks ..
