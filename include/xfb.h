@@ -117,7 +117,8 @@ int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cma
  * uses that stage's velocity, the tendency is dealiased and combined exactly like the vorticity's
  * (src/main.cpp:225-251,286-312 with c for vort and kappa for NU), so a tracer equal to the vorticity with
  * kappa == nu and no forcing stays bit-identical to it.  `tracer` is nx*ny floats, host or device; kappa is one value
- * per handle (the last call's).  Fused single-GPU grids only (power of two, <= 8192); XFB_E_SIZE otherwise.
+ * per handle (the last call's).  Single-GPU handles: power-of-two grids <= 8192 (fused kernels) and the generic
+ * mixed-radix sizes (e.g. 768); XFB_E_SIZE for 16384 and slab-decomposed handles.
  * Read back with xfb_get_field(..., XFB_TRACER, ...); effective-diffusivity histograms over the tracer: */
 int xfb_set_tracer(xfb_handle h, int member, const float *tracer, float kappa);
 int xfb_get_tracer_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cmax, double *area, double *grad2);

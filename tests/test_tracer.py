@@ -140,10 +140,29 @@ def test_tracer_error_paths():
     with pytest.raises(xfb.XfbError):
         b.tracer_keff_hist(16, 0.0, 1.0)
     b.close()
-    g = xfb.Backend(768)                           # generic mixed-radix path: no tracer
-    with pytest.raises(xfb.XfbError):
-        g.set_tracer(np.zeros((768, 768), np.float32), 1.0)
-    g.close()
+
+
+@pytest.mark.gpu
+def test_tracer_on_the_default_768_grid():
+    """generic mixed-radix path (the reference's default NPTS = 768): same loops, unfused"""
+    import xlab_fftbarotropic_b200 as xfb
+    from oracle import oracle as orc
+    n = 768
+    v0 = fields.elliptic(n)
+    c0 = _blob(n)
+    b = xfb.Backend(n)
+    o = orc.Oracle(n)
+    b.set_vorticity(v0); o.set_vorticity(v0)
+    b.set_tracer(c0, 20.0); o.set_tracer(c0, 20.0)
+    b.step(1, 3.0); o.step(1, 3.0)
+    assert rel_l2(b.get_field(xfb.capi.TRACER), o.get_tracer()) < 1e-5
+    b.step(9, 3.0); o.step(9, 3.0)
+    assert rel_l2(b.get_field(xfb.capi.TRACER), o.get_tracer()) < 1e-5
+    assert rel_l2(b.get_field(xfb.capi.VORT), o.get_field(orc.VORT)) < 1e-5
+    a_g, g_g = b.tracer_keff_hist(32, -0.01, 1.01)
+    a_o, g_o = o.tracer_keff_hist(32, -0.01, 1.01)
+    assert rel_l2(a_g, a_o) < 1e-3 and rel_l2(g_g, g_o) < 1e-3
+    b.close()
 
 
 @pytest.mark.gpu

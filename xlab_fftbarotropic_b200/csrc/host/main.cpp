@@ -9,7 +9,7 @@
 //   -n <NPTS=768> -d <dt=3> -t <total_steps=1200> -r <record_step=100> -L <600000> -N <NU=6.5>
 // Additions: -g <cuda device>, -D (also write filamentation time / deformation factor at record steps),
 //   -q (no per-step line), -c <tracer file> [-k <kappa>] (advect a passive tracer read from <input dir>, written as
-//   tracer_step_N.bin after the reference's five files; power-of-two grids only).
+//   tracer_step_N.bin after the reference's five files).
 // Record output is asynchronous: at a record step the five fields are formed on the GPU and copied
 // to pinned host buffers on a second stream (xfb_get_field_async) while the next stretch of steps already runs; a
 // writer thread waits for each buffer, calls writeField and appends the `log` line -- same files, same order as the

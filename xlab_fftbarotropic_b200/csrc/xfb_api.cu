@@ -634,8 +634,8 @@ extern "C" int xfb_set_tracer(xfb_handle h, int member, const float *tracer, flo
 {
     if (check_member(h, member)) return XFB_E_ARG;
     if (!tracer) return fail(XFB_E_ARG, "null tracer");
-    if (!fused_diag_ok(h))
-        return fail(XFB_E_SIZE, "the passive tracer runs on the fused single-GPU kernels only (power-of-two grids <= 8192, no slab)");
+    if (!fused_diag_ok(h) && !h->generic)
+        return fail(XFB_E_SIZE, "the passive tracer needs a single-GPU grid <= 8192 (fused kernels) or a generic mixed-radix grid");
     CK(cudaSetDevice(h->device));
     const size_t sb = sizeof(cpx) * h->hpad * h->batch;
     if (!h->c0) {
@@ -644,13 +644,19 @@ extern "C" int xfb_set_tracer(xfb_handle h, int member, const float *tracer, flo
             if (dev_alloc((void **)pp, sb)) return XFB_E_CUDA;
             CK(cudaMemsetAsync(*pp, 0, sb, h->stream));
         }
-        if (dev_alloc((void **)&h->tc[0], 2 * sb)) return XFB_E_CUDA;
-        CK(cudaMemsetAsync(h->tc[0], 0, 2 * sb, h->stream));
-        h->tc[1] = h->tc[0] + h->hpad * h->batch;
+        if (!h->generic) {
+            if (dev_alloc((void **)&h->tc[0], 2 * sb)) return XFB_E_CUDA;
+            CK(cudaMemsetAsync(h->tc[0], 0, 2 * sb, h->stream));
+            h->tc[1] = h->tc[0] + h->hpad * h->batch;
+        }
     }
     const void *din;
     if (stage_in(h, tracer, h->real_a, sizeof(float) * h->grids, &din)) return XFB_E_CUDA;
-    if (fused_forward_to_state(h, (const float *)din, h->c0 + (size_t)member * h->hpad)) return XFB_E_CUDA;
+    if (h->generic) {
+        if (fwd2d(h, (const float *)din, h->spec_a, h->spec_b)) return XFB_E_CUDA;
+        if (launch_pw(h, OP_COPY, h->spec_b, h->pitch, h->c0 + (size_t)member * h->hpad, h->pitch, h->pitch, 0, h->tw_state))
+            return XFB_E_CUDA;
+    } else if (fused_forward_to_state(h, (const float *)din, h->c0 + (size_t)member * h->hpad)) return XFB_E_CUDA;
     if (!h->has_tracer || h->kappa != kappa) {
         // the captured step has no tracer launches / another diffusivity baked in
         if (h->step_graph) { cudaGraphExecDestroy((cudaGraphExec_t)h->step_graph); h->step_graph = nullptr; }
@@ -756,17 +762,19 @@ extern "C" int xfb_step(xfb_handle h, int nsteps, float dt)
 }
 
 // derived spectral field of member -> physical field in `dout` (device), reference normalisation
-static int derived_field(xfb_handle h, int member, int which, float *dout)
+static int derived_field(xfb_handle h, int member, int which, float *dout, const cpx *state = nullptr)
 {
-    const cpx *z = h->z0 + (size_t)member * h->hpad;
+    if (which == XFB_TRACER) {
+        if (!h->has_tracer) return fail(XFB_E_STATE, "XFB_TRACER before xfb_set_tracer");
+        return derived_field(h, member, XFB_VORT, dout, h->c0);
+    }
+    const cpx *z = (state ? state : h->z0) + (size_t)member * h->hpad;
     const float scale = 1.0f / (float)((double)h->nx * (double)h->ny);
     const int P = h->pitch, T = h->tw_state;
-    if (which == XFB_TRACER && !h->has_tracer) return fail(XFB_E_STATE, "XFB_TRACER before xfb_set_tracer");
     if (fused_diag_ok(h)) {
         // record fields on the stepper's kernels: one K-COL launch (spectral multiplier + x pass, TMA-staged) and one
         // K-ROW launch (y pass, normalisation, sign); multipliers in float32 (<= 2 ulp from the operator tier's tables)
-        if (which == XFB_TRACER ? fused_products(h, member, 2 + XFB_VORT, 1, h->c0) : fused_products(h, member, 2 + which, 1))
-            return XFB_E_CUDA;
+        if (fused_products(h, member, 2 + which, 1, state)) return XFB_E_CUDA;
         RowParams r; fill_row(h, r, h->nx);
         r.spec_in[0] = h->dg; r.real_out = dout; r.scale = scale; r.negate = (which == XFB_U) ? 1 : 0;
         CKL(h, launch_row(h->ny, ROW_C2R, r, h->stream));
@@ -1039,9 +1047,9 @@ static int keff_hist_impl(xfb_handle h, int member, int nbins, float cmin, float
     if (fused) {
         if (fused_diag(h, member, 1, h->real_a, h->real_b, state)) return XFB_E_CUDA;       // c, |grad c|^2
     } else {
-        if (derived_field(h, member, XFB_VORT, h->real_a)) return XFB_E_CUDA;
-        if (derived_field(h, member, XFB_DVORTDX, h->real_b)) return XFB_E_CUDA;
-        if (derived_field(h, member, XFB_DVORTDY, h->real_c)) return XFB_E_CUDA;
+        if (derived_field(h, member, XFB_VORT, h->real_a, state)) return XFB_E_CUDA;
+        if (derived_field(h, member, XFB_DVORTDX, h->real_b, state)) return XFB_E_CUDA;
+        if (derived_field(h, member, XFB_DVORTDY, h->real_c, state)) return XFB_E_CUDA;
     }
     double *d = (double *)h->ref_a;
     CK(cudaMemsetAsync(d, 0, sizeof(double) * 2 * nbins, h->stream));

@@ -287,6 +287,18 @@ int generic_step(xfb_handle h, int nsteps, float dt)
                 if (generic_fwd2d(h, fa, tmp2, T)) return XFB_E_CUDA;                                                                // :237
                 GLAUNCH(h, (gen_stage<<<hb, 256, 0, h->stream>>>(T, z0, zk, acc, h->nx, h->hy, h->kx2, h->ky2, h->mask_kd, h->nu, dt,
                                                                   (k == 3) ? dt : dt / 2.0f, k)));
+                if (h->has_tracer) {
+                    // passive tracer (xfb_set_tracer): the same loops with c for vort and kappa for NU; -u, v of this
+                    // stage are still in fc, fd
+                    cpx *c0 = h->c0 + (size_t)m * h->hpad, *ck = h->ck + (size_t)m * h->hpad, *cacc = h->cacc + (size_t)m * h->hpad;
+                    const cpx *c = (k == 1) ? c0 : ck;
+                    if (launch_pw(h, OP_GRADX, c, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fa, scale, 0)) return XFB_E_CUDA;
+                    if (launch_pw(h, OP_GRADY, c, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fb, scale, 0)) return XFB_E_CUDA;
+                    GLAUNCH(h, (gen_jacobian<<<gb, 256, 0, h->stream>>>(fc, fa, fd, fb, nullptr, fa, n)));
+                    if (generic_fwd2d(h, fa, tmp2, h->cjint)) return XFB_E_CUDA;
+                    GLAUNCH(h, (gen_stage<<<hb, 256, 0, h->stream>>>(h->cjint, c0, ck, cacc, h->nx, h->hy, h->kx2, h->ky2, h->mask_kd,
+                                                                      h->kappa, dt, (k == 3) ? dt : dt / 2.0f, k)));
+                }
             }
     }
     return 0;
