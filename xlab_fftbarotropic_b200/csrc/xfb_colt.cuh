@@ -39,6 +39,10 @@ struct ColTCfg {
     static constexpr bool SPLIT_IN = (2 * S_BYTES + F_BYTES + 1024 <= 227 * 1024);
     static constexpr int SMEM = (SPLIT_IN ? 2 : 1) * S_BYTES + F_BYTES + 1024;                // + alignment slack
     static constexpr int MINB = (THREADS >= 512) ? 1 : (THREADS >= 256) ? 2 : 4;
+    // NG > 1 (8192): the new stage state of the tile's columns cannot stay in registers across the column groups; it
+    // is parked in TENSOR MEMORY (each thread's own 32 columns per column group, tcgen05.st / tcgen05.ld) instead of
+    // being re-read from global memory for each of the four products
+    static constexpr int TCOLS = (THREADS / 128) * NG * 32;
     static_assert(THREADS >= 32 && THREADS <= 512, "bad column-group size");
 };
 
@@ -57,6 +61,8 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
     constexpr int MODE = (MODE_ == COL_TSTEP) ? COL_STEP : (MODE_ == COL_TPRO) ? COL_PRO : MODE_;
     constexpr int G = C::G, TW = C::TW, FW = C::FW, NG = C::NG;
     constexpr bool KEEP = (NG == 1);
+    constexpr bool TKEEP = (NG > 1) && (MODE == COL_STEP) && (C::THREADS % 128 == 0) && (C::TCOLS >= 32) && (C::TCOLS <= 512) &&
+                           ((C::TCOLS & (C::TCOLS - 1)) == 0);
     extern __shared__ unsigned char smem_dyn[];
     // TMA needs 128-byte aligned shared addresses
     unsigned char *smem_raw = smem_dyn + ((1024 - (smem_u32(smem_dyn) & 1023)) & 1023);
@@ -64,6 +70,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
     cpx *F = reinterpret_cast<cpx *>(smem_raw + C::S_BYTES);
     cpx *SI = C::SPLIT_IN ? reinterpret_cast<cpx *>(smem_raw + C::S_BYTES + C::F_BYTES) : S;   // incoming tendency tile
     __shared__ unsigned long long full;
+    __shared__ unsigned tmem_slot;
 
     const int tid = threadIdx.x;
     int t[1], c[1];
@@ -76,6 +83,12 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
         mbar_fence_init();
     }
     __syncthreads();
+    unsigned tbase = 0, tpark = 0;
+    if (TKEEP) {
+        tbase = tmem_alloc_cta<TKEEP ? C::TCOLS : 32>(&tmem_slot);
+        const int warp = tid >> 5;
+        tpark = tbase + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * (NG * 32));     // + cg * 32
+    }
     unsigned phase = 0;
     const size_t srow = (size_t)p.st_row_stride;
 
@@ -83,6 +96,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
     const int s_base = ((t[0] >> 1) * TW) * 2 + (t[0] & 1);
 
     constexpr bool HAS_FWD = (MODE == COL_STEP || MODE == COL_FWDT);
+    constexpr bool PIPE_TAIL = (MODE == COL_STEP) && !C::SPLIT_IN && (C::NBOX > 1) && (C::NBOX <= 16);
     int tile = blockIdx.x;
     if (HAS_FWD && tile < tiles_total && tid == 0) {
         const int member = tile / tiles_per_member, tl = tile - member * tiles_per_member;
@@ -148,6 +162,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
 #pragma unroll
                         for (int q = 0; q < 8; ++q) { zkv[q] = z0v[q]; av[q] = mk(0.f, 0.f); }
                     }
+                    cpx znew[TKEEP ? 8 : 1];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int k = 8 * h + q;
@@ -178,7 +193,9 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
                             p.zk[e] = zn;
                         }
                         if (KEEP) zkeep[k] = zn;
+                        if (TKEEP) znew[q] = zn;
                     }
+                    if (TKEEP) tmem_park8(tpark + (unsigned)(cg * 32 + h * 16), reinterpret_cast<const cpx(&)[8]>(znew));
                 }
             }
         }
@@ -211,7 +228,9 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
                 const int j = p.j_base + j0 + col;
                 const float ky = __ldg(p.ky + j);
                 const float ky2 = ky * ky;
-                if (!KEEP) {
+                if (TKEEP) {
+                    tmem_unpark(tpark + (unsigned)(cg * 32), v[0]);
+                } else if (!KEEP) {
                     const size_t e0 = moff + (size_t)(tl * NG + cg) * (size_t)p.st_tile_stride + (size_t)t[0] * srow + c[0];
 #pragma unroll
                     for (int k = 0; k < 16; ++k) v[0][k] = zsrc[e0 + (size_t)(k * G) * srow];
@@ -272,9 +291,19 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
             __syncthreads();
             if (tid == 0) {
                 const CUtensorMap *mt = &maps.t[f];
+                if (PIPE_TAIL && f == NF - 1) {
+                    // last field of the tile: one bulk group per box, so that the next tile's boxes can be fetched as the
+                    // store engine releases them (below)
 #pragma unroll 1
-                for (int b = 0; b < C::NBOX; ++b) tma_store_2d(mt, tmx, tmy + b * C::BOXR, S + (size_t)b * C::BOXR * TW * 2);
-                tma_commit();
+                    for (int b = 0; b < C::NBOX; ++b) {
+                        tma_store_2d(mt, tmx, tmy + b * C::BOXR, S + (size_t)b * C::BOXR * TW * 2);
+                        tma_commit();
+                    }
+                } else {
+#pragma unroll 1
+                    for (int b = 0; b < C::NBOX; ++b) tma_store_2d(mt, tmx, tmy + b * C::BOXR, S + (size_t)b * C::BOXR * TW * 2);
+                    tma_commit();
+                }
             }
         }
 
@@ -283,15 +312,25 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
             const int nt = tile + gridDim.x;
             if (nt < tiles_total && tid == 0) {
                 const int nm = nt / tiles_per_member, ntl = nt - nm * tiles_per_member;
-                tma_wait_read_all();
                 mbar_expect_tx(&full, C::S_BYTES);
+                if (PIPE_TAIL) {
+                    // box b of the incoming tile as soon as the store of box b (bulk group b of the last NBOX) has read it
+#pragma unroll
+                    for (int b = 0; b < C::NBOX; ++b) {
+                        tma_wait_read_n(C::NBOX - 1 - b);
+                        tma_load_2d(S + (size_t)b * C::BOXR * TW * 2, &maps.jint, ntl * TW * 2, nm * (NX / 2) + b * C::BOXR, &full);
+                    }
+                } else {
+                    tma_wait_read_all();
 #pragma unroll 1
-                for (int b = 0; b < C::NBOX; ++b)
-                    tma_load_2d(S + (size_t)b * C::BOXR * TW * 2, &maps.jint, ntl * TW * 2, nm * (NX / 2) + b * C::BOXR, &full);
+                    for (int b = 0; b < C::NBOX; ++b)
+                        tma_load_2d(S + (size_t)b * C::BOXR * TW * 2, &maps.jint, ntl * TW * 2, nm * (NX / 2) + b * C::BOXR, &full);
+                }
             }
         }
     }
     if (tid == 0) tma_wait_all();
+    if (TKEEP) tmem_free_cta<TKEEP ? C::TCOLS : 32>(tbase);
 }
 
 }  // namespace xfb

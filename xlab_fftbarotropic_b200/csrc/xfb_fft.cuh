@@ -97,6 +97,21 @@ __device__ __forceinline__ void tma_prefetch_2d(const void *map, int x, int y)
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores have finished READING shared memory (the buffer may be overwritten)
 __device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the N most recent committed bulk groups have finished reading shared memory
+template <int N>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// the same with a loop counter (0..15) that is constant after unrolling
+__device__ __forceinline__ void tma_wait_read_n(const int n)
+{
+    switch (n) {
+    case 0: tma_wait_read<0>(); break;   case 1: tma_wait_read<1>(); break;   case 2: tma_wait_read<2>(); break;
+    case 3: tma_wait_read<3>(); break;   case 4: tma_wait_read<4>(); break;   case 5: tma_wait_read<5>(); break;
+    case 6: tma_wait_read<6>(); break;   case 7: tma_wait_read<7>(); break;   case 8: tma_wait_read<8>(); break;
+    case 9: tma_wait_read<9>(); break;   case 10: tma_wait_read<10>(); break; case 11: tma_wait_read<11>(); break;
+    case 12: tma_wait_read<12>(); break; case 13: tma_wait_read<13>(); break; case 14: tma_wait_read<14>(); break;
+    default: tma_wait_read<15>(); break;
+    }
+}
 // all committed bulk stores are complete (global memory written)
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -134,6 +149,15 @@ __device__ __forceinline__ void tmem_park(unsigned taddr, const cpx (&r)[16])
         "f"(r[5].x), "f"(r[5].y), "f"(r[6].x), "f"(r[6].y), "f"(r[7].x), "f"(r[7].y), "f"(r[8].x), "f"(r[8].y), "f"(r[9].x), "f"(r[9].y),
         "f"(r[10].x), "f"(r[10].y), "f"(r[11].x), "f"(r[11].y), "f"(r[12].x), "f"(r[12].y), "f"(r[13].x), "f"(r[13].y), "f"(r[14].x),
         "f"(r[14].y), "f"(r[15].x), "f"(r[15].y)
+        : "memory");
+}
+// 8 complex registers -> 16 columns
+__device__ __forceinline__ void tmem_park8(unsigned taddr, const cpx (&r)[8])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "f"(r[0].x), "f"(r[0].y), "f"(r[1].x), "f"(r[1].y), "f"(r[2].x), "f"(r[2].y), "f"(r[3].x), "f"(r[3].y), "f"(r[4].x), "f"(r[4].y),
+        "f"(r[5].x), "f"(r[5].y), "f"(r[6].x), "f"(r[6].y), "f"(r[7].x), "f"(r[7].y)
         : "memory");
 }
 // the stores above complete asynchronously; a load of what they wrote waits for them first
