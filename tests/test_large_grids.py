@@ -97,11 +97,12 @@ def _run_variant(n, dt, env, out):
     return np.load(out)
 
 
-@pytest.mark.parametrize("n,dt", [(4096, 1.0), (8192, 0.5)])
+@pytest.mark.parametrize("n,dt", [(1024, 3.0), (4096, 1.0), (8192, 0.5)])
 def test_kernel_generations_agree(n, dt, tmp_path):
     ref = _run_variant(n, dt, {}, str(tmp_path / "default.npy"))
     assert np.isfinite(ref.view(np.float32)).all()
-    variants = [{"XFB_ROW_SINGLE": "1", "XFB_COL_GEN1": "1"}, {"XFB_ROW_TMEM": "1"}]
+    # K-ROW with tensor-memory parks is the default at 8192 only: force it on and off everywhere
+    variants = [{"XFB_ROW_SINGLE": "1", "XFB_COL_GEN1": "1"}, {"XFB_ROW_TMEM": "1"}, {"XFB_ROW_TMEM": "0"}]
     if n == 8192:
         variants.append({"XFB_COL_CLUSTER": "1"})
     for env in variants:

@@ -87,9 +87,14 @@ __device__ __forceinline__ int signed_row(const int t, const int k)
 
 template <int NX, int W, int NIT>
 __device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&t)[NIT], const int (&c)[NIT],
-                                        const LineTw<NX> (&tw)[NIT])
+                                        const LineTw<NX> (&tw)[NIT], const bool drain_tma = false)
 {
     typedef LinePlan<NX> P;
+    // drain_tma (uniform over the CTA): the caller is going to overwrite a buffer that bulk stores may still be reading.
+    // Thread 0 waits for them as late as possible -- before the first barrier of the LAST exchange --, so the stores
+    // drain under the earlier passes and every thread that leaves the transform knows the buffer is free.
+    constexpr int LAST_EX = (P::NPASS > P::N16) ? P::N16 - 1 : P::N16 - 2;
+    if (LAST_EX < 0 && drain_tma && threadIdx.x == 0) tma_wait_read_all();
     int ns = 1;
 #pragma unroll
     for (int p = 0; p < P::N16; ++p) {
@@ -98,6 +103,7 @@ __device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&
         if (p != P::NPASS - 1) {
 #pragma unroll
             for (int it = 0; it < NIT; ++it) exchange_write<W>(v[it], sm, t[it], c[it], ns);
+            if (p == LAST_EX && drain_tma && threadIdx.x == 0) tma_wait_read_all();
             __syncthreads();
 #pragma unroll
             for (int it = 0; it < NIT; ++it) exchange_read<P::G, W>(v[it], sm, t[it], c[it]);

@@ -280,9 +280,8 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
                     v[0][k] = mk(z.x * kk, -z.y * kk);       // swap(i kk z)
                 }
                 // S is about to be overwritten: the bulk store of the previous field (or tile) must have read it.
-                // Thread 0 waits before the transform's first barrier, so every thread past that barrier knows.
-                if (cg == 0 && tid == 0) tma_wait_read_all();
-                col_fft<NX, FW, 1>(v, F, t, c, tw);
+                // Thread 0 waits inside the transform, before its last exchange barrier (col_fft, drain_tma).
+                col_fft<NX, FW, 1>(v, F, t, c, tw, cg == 0);
                 cpx *dst = S + s_base + 2 * col;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) dst[k * G * TW] = cswap(v[0][k]);

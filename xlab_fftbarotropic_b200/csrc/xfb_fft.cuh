@@ -160,6 +160,20 @@ __device__ __forceinline__ void tmem_park8(unsigned taddr, const cpx (&r)[8])
         "f"(r[5].x), "f"(r[5].y), "f"(r[6].x), "f"(r[6].y), "f"(r[7].x), "f"(r[7].y)
         : "memory");
 }
+// 16 columns -> 8 complex registers; waits for this thread's earlier stores and for the load itself inside ONE asm
+// statement, so no use of the result can be scheduled ahead of the wait.  Eight values at a time keep the register
+// peak at 16 + the consumer's state (a 32-register LDTM next to a live butterfly set spills).
+__device__ __forceinline__ void tmem_unpark8(unsigned taddr, cpx (&r)[8])
+{
+    asm volatile(
+        "tcgen05.wait::st.sync.aligned;\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=f"(r[0].x), "=f"(r[0].y), "=f"(r[1].x), "=f"(r[1].y), "=f"(r[2].x), "=f"(r[2].y), "=f"(r[3].x), "=f"(r[3].y), "=f"(r[4].x),
+          "=f"(r[4].y), "=f"(r[5].x), "=f"(r[5].y), "=f"(r[6].x), "=f"(r[6].y), "=f"(r[7].x), "=f"(r[7].y)
+        : "r"(taddr)
+        : "memory");
+}
 // the stores above complete asynchronously; a load of what they wrote waits for them first
 __device__ __forceinline__ void tmem_unpark(unsigned taddr, cpx (&r)[16])
 {

@@ -60,9 +60,11 @@ static int launch_pair_t(const RowParams &p, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
-// ROW_JAC with TMEM parks and double-buffered staging: opt-in (XFB_ROW_TMEM=1).  Correct, but measured SLOWER than the
-// shared-memory parks (8192^2: 0.62 vs 0.58 ms per launch, 4096^2: 0.16 vs 0.13): the extra live state (TMEM
-// addresses, two-buffer bookkeeping) pushes the transform core over 128 registers (300 bytes of spills per thread).
+// ROW_JAC with the parked products in TENSOR MEMORY and double-buffered staging.  Default at NY = 8192, where the
+// shared-memory parks leave room for one staging buffer only (0.52 vs 0.58 ms per launch at 8192^2); at 4096 and below
+// two CTAs per SM already hide the fetches and the shared-memory parks are faster (4096^2: 0.136 vs 0.126 ms).
+// XFB_ROW_TMEM=0 / 1 forces either kernel (A/B knob).  The first version moved 32 registers per tcgen05.ld / st and
+// spilled 300 bytes per thread (0.62 ms); halves of 16 registers do not.
 template <int NY>
 static int launch_pair_tmem(const RowParams &p, cudaStream_t st)
 {
@@ -85,10 +87,10 @@ static int launch_pair_tmem(const RowParams &p, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
-static bool use_tmem_parks()
+static bool use_tmem_parks(int ny)
 {
-    static const bool on = getenv("XFB_ROW_TMEM") && atoi(getenv("XFB_ROW_TMEM")) != 0;
-    return on;
+    static const int forced = getenv("XFB_ROW_TMEM") ? (atoi(getenv("XFB_ROW_TMEM")) != 0 ? 1 : 0) : -1;
+    return forced >= 0 ? forced == 1 : ny == 8192;
 }
 
 // XFB_ROW_SINGLE=1 forces the one-row-per-line kernel (tuning / A-B knob); 16384 always uses it
@@ -108,7 +110,7 @@ static int launch_row_n(int mode, const RowParams &p, cudaStream_t st)
             case ROW_R2C: return dist ? launch_pair_t<NY, ROW_R2C, true>(p, st) : launch_pair_t<NY, ROW_R2C, false>(p, st);
             case ROW_C2R: return dist ? launch_pair_t<NY, ROW_C2R, true>(p, st) : launch_pair_t<NY, ROW_C2R, false>(p, st);
             case ROW_JAC:
-                if (!dist && use_tmem_parks()) return launch_pair_tmem<NY>(p, st);
+                if (!dist && use_tmem_parks(NY)) return launch_pair_tmem<NY>(p, st);
                 return dist ? launch_pair_t<NY, ROW_JAC, true>(p, st) : launch_pair_t<NY, ROW_JAC, false>(p, st);
             case ROW_DIAG: return dist ? (int)cudaErrorInvalidValue : launch_pair_t<NY, ROW_DIAG, false>(p, st);
             }

@@ -295,32 +295,40 @@ rowpair_jac_tmem_kernel(const RowParams p)
             bar.sync();                 // everyone has read this staging buffer: refill it two fields ahead
             XFB_FETCH(n + 2);
             line_fft<NY, 1>(v, sm, t, 0, tw, bar);
-            // v = (b[n], a[n]) unscaled, swapped: .y is row 2m, .x row 2m+1
-            if (f == 0) {
+            // v = (b[n], a[n]) unscaled, swapped: .y is row 2m, .x row 2m+1.  Tensor-memory traffic in halves of
+            // eight values (16 registers) so that nothing spills next to the live butterfly set.
+            if (f == 0 || f == 2) {
+                const unsigned park = (f == 0) ? park0 : park1;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = mk(v[q].y * p.scale, v[q].x * p.scale);      // -u
-                tmem_park(park0, v);
+                for (int h = 0; h < 2; ++h) {
+                    cpx a[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) a[q] = mk(v[8 * h + q].y * p.scale, v[8 * h + q].x * p.scale);      // -u ; v
+                    tmem_park8(park + 16 * h, a);
+                }
             } else if (f == 1) {
-                cpx a[16];
-                tmem_unpark(park0, a);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) a[q] = mk(a[q].x * (v[q].y * p.scale), a[q].y * (v[q].x * p.scale));   // -u dvortdx
-                tmem_park(park0, a);
-            } else if (f == 2) {
+                for (int h = 0; h < 2; ++h) {
+                    cpx a[8];
+                    tmem_unpark8(park0 + 16 * h, a);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = mk(v[q].y * p.scale, v[q].x * p.scale);      // v
-                tmem_park(park1, v);
+                    for (int q = 0; q < 8; ++q)
+                        a[q] = mk(a[q].x * (v[8 * h + q].y * p.scale), a[q].y * (v[8 * h + q].x * p.scale));           // -u dvortdx
+                    tmem_park8(park0 + 16 * h, a);
+                }
             }
         }
-        // J = (-u dvortdx) - v dvortdy, formed in place in v (two register sets live, not three)   main.cpp:225-227
-        {
-            cpx a[16];
-            tmem_unpark(park1, a);
+        // J = (-u dvortdx) - v dvortdy, formed in place in v                                       main.cpp:225-227
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = mk(a[q].x * (v[q].y * p.scale), a[q].y * (v[q].x * p.scale));      // v dvortdy
-            tmem_unpark(park0, a);
+        for (int h = 0; h < 2; ++h) {
+            cpx a[8];
+            tmem_unpark8(park1 + 16 * h, a);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = mk(a[q].x - v[q].x, a[q].y - v[q].y);
+            for (int q = 0; q < 8; ++q)
+                v[8 * h + q] = mk(a[q].x * (v[8 * h + q].y * p.scale), a[q].y * (v[8 * h + q].x * p.scale));          // v dvortdy
+            tmem_unpark8(park0 + 16 * h, a);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[8 * h + q] = mk(a[q].x - v[8 * h + q].x, a[q].y - v[8 * h + q].y);
         }
         if (p.real_in != nullptr) {
             const float *sa = p.real_in + ro, *sb = sa + NY;
