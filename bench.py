@@ -359,7 +359,7 @@ def gpu_arm(args):
     step_gbs = ALGO_BYTES_PER_PT_STEP * value / world / 1e9
     traffic, traffic_src = measured_traffic(n, "col_step" if dominant == "col" else "row_jac") if args.members == 1 else (None, None)
     names = {"col": "colt_kernel<COL_STEP>" if n <= 8192 else "col_kernel<COL_STEP>",
-             "row": "rowpair_kernel<ROW_JAC>" if n <= 8192 else "row_kernel<ROW_JAC>"}
+             "row": ("rowpair_jac_tmem_kernel" if n == 8192 else "rowpair_kernel<ROW_JAC>") if n <= 8192 else "row_kernel<ROW_JAC>"}
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "traffic_source": traffic_src, "kernel": names[dominant],
