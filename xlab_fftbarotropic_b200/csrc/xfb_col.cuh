@@ -85,9 +85,16 @@ __device__ __forceinline__ int signed_row(const int t, const int k)
     return i - NX;
 }
 
-template <int NX, int W, int NIT>
+// no-op hook of col_fft
+struct ColFftNoHook {
+    __device__ __forceinline__ void operator()(int, bool) const {}
+};
+
+// hook(e, last): called by every thread after exchange e (0-based) has been read and its closing barrier passed --
+// a CTA-uniform point between two barriers where the caller can slip in unrelated pipelined work.
+template <int NX, int W, int NIT, class Hook>
 __device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&t)[NIT], const int (&c)[NIT],
-                                        const LineTw<NX> (&tw)[NIT], const bool drain_tma = false)
+                                        const LineTw<NX> (&tw)[NIT], const bool drain_tma, Hook &hook)
 {
     typedef LinePlan<NX> P;
     // drain_tma (uniform over the CTA): the caller is going to overwrite a buffer that bulk stores may still be reading.
@@ -108,11 +115,20 @@ __device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&
 #pragma unroll
             for (int it = 0; it < NIT; ++it) exchange_read<P::G, W>(v[it], sm, t[it], c[it]);
             __syncthreads();
+            hook(p, p == LAST_EX);
         }
         ns *= 16;
     }
 #pragma unroll
     for (int it = 0; it < NIT; ++it) rem_pass<NX>(v[it], tw[it]);
+}
+
+template <int NX, int W, int NIT>
+__device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&t)[NIT], const int (&c)[NIT],
+                                        const LineTw<NX> (&tw)[NIT], const bool drain_tma = false)
+{
+    ColFftNoHook nohook;
+    col_fft<NX, W, NIT, ColFftNoHook>(v, sm, t, c, tw, drain_tma, nohook);
 }
 
 template <int NX, int W, int MODE>

@@ -37,18 +37,85 @@ struct ColTCfg {
     // fetched during the whole current tile.  At 8192 one buffer serves both directions (pulling the next tile
     // into L2 early -- prefetch.global.L2 or cp.async.bulk.prefetch.tensor -- was measured SLOWER: 0.96 vs 0.92 ms).
     static constexpr bool SPLIT_IN = (2 * S_BYTES + F_BYTES + 1024 <= 227 * 1024);
-    static constexpr int SMEM = (SPLIT_IN ? 2 : 1) * S_BYTES + F_BYTES + 1024;                // + alignment slack
+    // 8192: no room for a second staging buffer.  The NEXT tile is streamed in, box by box, through a small ring of
+    // TMA boxes and parked in TENSOR MEMORY (each thread keeps the 2 x 16 values it will feed to the forward
+    // transforms in its own TMEM lane) while the current tile's inverse transforms run; see ColtRing below.
+#ifndef XFB_COLT_NO_RING
+    static constexpr bool RING = !SPLIT_IN && (TW / FW == 2) && ((NX / 2) / BOXR == 16) && (G * FW == 512);
+#else
+    static constexpr bool RING = false;
+#endif
+    static constexpr int RING_SLOTS = 3;
+    static constexpr int BOX_BYTES = BOXR * TW * 2 * (int)sizeof(cpx);
+    static constexpr int SMEM = (SPLIT_IN ? 2 : 1) * S_BYTES + F_BYTES + (RING ? RING_SLOTS * BOX_BYTES : 0) + 1024;   // + alignment slack
     static constexpr int MINB = (THREADS >= 512) ? 1 : (THREADS >= 256) ? 2 : 4;
     // NG > 1 (8192): the new stage state of the tile's columns cannot stay in registers across the column groups; it
     // is parked in TENSOR MEMORY (each thread's own 32 columns per column group, tcgen05.st / tcgen05.ld) instead of
     // being re-read from global memory for each of the four products
     static constexpr int TCOLS = (THREADS / 128) * NG * 32;
+    static_assert(RING_SLOTS == 3, "ColtRing counts modulo 3");
     static_assert(THREADS >= 32 && THREADS <= 512, "bad column-group size");
 };
 
 struct ColTMaps {
     CUtensorMap jint;
     CUtensorMap t[4];
+};
+
+// Streaming of the next tile into tensor memory (ColTCfg::RING).  Box q of a tile = row pairs [256 q, 256 q + 256) x TW
+// columns = rows [512 q, 512 q + 512): exactly ONE row of every butterfly thread (its k = q).  The hook of col_fft
+// calls step() at two barrier-separated points of each of the eight inverse transforms of a tile = 16 points:
+//   thread 0 issues the TMA load of box q + 2 into the slot box q - 1 left (everyone read it before the last barrier),
+//   every thread waits for box q and copies its two values (one per column) from the ring into its TMEM lane.
+// Box counters run on over the tiles of the CTA (slot = counter mod 3, mbarrier parity = (counter / 3) & 1).
+// Issuing earlier (three boxes at the start, the next box ahead of each field's bulk stores) was measured slower
+// (0.821 vs 0.795 ms per launch): the loads then delay the stores the next transform has to wait for.
+template <int NX>
+struct ColtRing {
+    typedef ColTCfg<NX> C;
+    static constexpr int BOX_ELEMS = C::BOX_BYTES / (int)sizeof(cpx);
+    const CUtensorMap *map;
+    cpx *ring;
+    unsigned long long *bar;
+    int s_off;            // this thread's element of a box: ((t >> 1) * TW) * 2 + (t & 1), + 2 * column
+    unsigned tin;         // this thread's incoming TMEM region: + cg * 32 + 2 * q
+    int cx, cy;           // TMA coordinates of box 0 of the tile being streamed in
+    int q;                // next box of that tile to consume; >= 16: nothing to do
+    int slot;             // ring slot of box q
+    unsigned parity;      // mbarrier parity of that slot's current use
+
+    __device__ __forceinline__ void issue(const int box, const int sl) const     // thread 0
+    {
+        mbar_expect_tx(bar + sl, (unsigned)C::BOX_BYTES);
+        tma_load_2d(ring + (size_t)sl * BOX_ELEMS, map, cx, cy + box * C::BOXR, bar + sl);
+    }
+    // start streaming the tile at TMA coordinates (x, y): boxes 0 and 1 (their slots are free: barriers have passed
+    // since the previous tile's last boxes were consumed)
+    __device__ __forceinline__ void begin(const int x, const int y)
+    {
+        cx = x; cy = y; q = 0;
+        if (threadIdx.x == 0) {
+            issue(0, slot);
+            issue(1, slot == 2 ? 0 : slot + 1);
+        }
+    }
+    // right behind a CTA barrier that follows the previous step()
+    __device__ __forceinline__ void step()
+    {
+        if (q >= 16) return;
+        if (threadIdx.x == 0 && q + 2 < 16) issue(q + 2, slot == 0 ? 2 : slot - 1);      // (slot + 2) mod 3
+        mbar_wait(bar + slot, parity);
+        const cpx *src = ring + (size_t)slot * BOX_ELEMS + s_off;
+        const cpx a = src[0], b = src[2];
+        tmem_park1(tin + (unsigned)(2 * q), a);
+        tmem_park1(tin + (unsigned)(32 + 2 * q), b);
+        ++q;
+        if (slot == 2) { slot = 0; parity ^= 1u; } else ++slot;
+    }
+    __device__ __forceinline__ void operator()(const int e, const bool last)
+    {
+        if (e == 0 || last) step();
+    }
 };
 
 template <int NX, int MODE_>
@@ -69,7 +136,10 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
     cpx *S = reinterpret_cast<cpx *>(smem_raw);                                   // outgoing products (and incoming tile if !SPLIT_IN)
     cpx *F = reinterpret_cast<cpx *>(smem_raw + C::S_BYTES);
     cpx *SI = C::SPLIT_IN ? reinterpret_cast<cpx *>(smem_raw + C::S_BYTES + C::F_BYTES) : S;   // incoming tendency tile
+    constexpr bool TRING = C::RING && TKEEP && !TRACER;       // the tracer step has 4 inverse transforms: too few hook points
+    constexpr int TMEM_COLS = TRING ? 512 : (TKEEP ? C::TCOLS : 32);
     __shared__ unsigned long long full;
+    __shared__ unsigned long long ring_bar[C::RING_SLOTS];
     __shared__ unsigned tmem_slot;
 
     const int tid = threadIdx.x;
@@ -80,25 +150,46 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
     tw[0].init(p.tw, p.twn, t[0]);
     if (tid == 0) {
         mbar_init(&full, 1);
+        for (int i = 0; i < C::RING_SLOTS; ++i) mbar_init(&ring_bar[i], 1);
         mbar_fence_init();
     }
     __syncthreads();
     unsigned tbase = 0, tpark = 0;
     if (TKEEP) {
-        tbase = tmem_alloc_cta<TKEEP ? C::TCOLS : 32>(&tmem_slot);
+        tbase = tmem_alloc_cta<TMEM_COLS>(&tmem_slot);
         const int warp = tid >> 5;
         tpark = tbase + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * (NG * 32));     // + cg * 32
+    }
+    ColtRing<NX> rs;
+    if (TRING) {
+        const int warp = tid >> 5;
+        rs.map = &maps.jint;
+        rs.ring = reinterpret_cast<cpx *>(smem_raw + C::S_BYTES + C::F_BYTES);
+        rs.bar = ring_bar;
+        rs.tin = tbase + ((unsigned)(32 * (warp & 3)) << 16) + 256u + (unsigned)((warp >> 2) * 64);
+        rs.slot = 0; rs.parity = 0; rs.q = 16; rs.cx = 0; rs.cy = 0;
     }
     unsigned phase = 0;
     const size_t srow = (size_t)p.st_row_stride;
 
     // element (row i = t + k*G, tile column col) of S: ((i >> 1) * TW + col) * 2 + (i & 1); k-stride = G * TW
     const int s_base = ((t[0] >> 1) * TW) * 2 + (t[0] & 1);
+    if (TRING) rs.s_off = s_base;
 
     constexpr bool HAS_FWD = (MODE == COL_STEP || MODE == COL_FWDT);
-    constexpr bool PIPE_TAIL = (MODE == COL_STEP) && !C::SPLIT_IN && (C::NBOX > 1) && (C::NBOX <= 16);
+    constexpr bool PIPE_TAIL = (MODE == COL_STEP) && !C::SPLIT_IN && (C::NBOX > 1) && (C::NBOX <= 16) && !TRING;
     int tile = blockIdx.x;
-    if (HAS_FWD && tile < tiles_total && tid == 0) {
+    if (TRING && tile < tiles_total) {
+        // the CTA's first tile: streamed into tensor memory with nothing to hide behind
+        const int member = tile / tiles_per_member, tl = tile - member * tiles_per_member;
+        rs.begin(tl * TW * 2, member * (NX / 2));
+#pragma unroll 1
+        for (int b = 0; b < 16; ++b) {
+            rs.step();
+            __syncthreads();
+        }
+    }
+    if (HAS_FWD && !TRING && tile < tiles_total && tid == 0) {
         const int member = tile / tiles_per_member, tl = tile - member * tiles_per_member;
         mbar_expect_tx(&full, C::S_BYTES);
 #pragma unroll 1
@@ -128,14 +219,20 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
                     }
                 }
             }
-            mbar_wait(&full, phase);
-            phase ^= 1;
+            if (!TRING) {
+                mbar_wait(&full, phase);
+                phase ^= 1;
+            }
 #pragma unroll 1
             for (int cg = 0; cg < NG; ++cg) {
                 const int col = cg * FW + c[0];
-                const cpx *src = SI + s_base + 2 * col;
+                if (TRING) {
+                    tmem_unpark(rs.tin + (unsigned)(cg * 32), v[0]);       // this tile was parked while the previous one ran
+                } else {
+                    const cpx *src = SI + s_base + 2 * col;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) v[0][k] = src[k * G * TW];
+                    for (int k = 0; k < 16; ++k) v[0][k] = src[k * G * TW];
+                }
                 col_fft<NX, FW, 1>(v, F, t, c, tw);
                 const int j = p.j_base + j0 + col;
                 const float kyv = __ldg(p.ky + j);
@@ -200,6 +297,17 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
             }
         }
 
+        if (TRING) {
+            // both columns have left the incoming TMEM region (the forward transforms' barriers are behind every
+            // thread): stream the next tile of this CTA into it under the eight inverse transforms below
+            const int nt = tile + gridDim.x;
+            if (nt < tiles_total) {
+                const int nm = nt / tiles_per_member, ntl = nt - nm * tiles_per_member;
+                rs.begin(ntl * TW * 2, nm * (NX / 2));
+            } else {
+                rs.q = 16;
+            }
+        }
         if (HAS_FWD && C::SPLIT_IN) {
             // every thread has read SI (it is behind the forward transform's barriers): fetch the next tile now
             const int nt = tile + gridDim.x;
@@ -281,7 +389,8 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
                 }
                 // S is about to be overwritten: the bulk store of the previous field (or tile) must have read it.
                 // Thread 0 waits inside the transform, before its last exchange barrier (col_fft, drain_tma).
-                col_fft<NX, FW, 1>(v, F, t, c, tw, cg == 0);
+                if (TRING) col_fft<NX, FW, 1, ColtRing<NX>>(v, F, t, c, tw, cg == 0, rs);
+                else col_fft<NX, FW, 1>(v, F, t, c, tw, cg == 0);
                 cpx *dst = S + s_base + 2 * col;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) dst[k * G * TW] = cswap(v[0][k]);
@@ -307,7 +416,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
         }
 
         // single staging buffer: next tile's tendency into S as soon as the last store has read it
-        if (HAS_FWD && !C::SPLIT_IN) {
+        if (HAS_FWD && !C::SPLIT_IN && !TRING) {
             const int nt = tile + gridDim.x;
             if (nt < tiles_total && tid == 0) {
                 const int nm = nt / tiles_per_member, ntl = nt - nm * tiles_per_member;
@@ -329,7 +438,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
         }
     }
     if (tid == 0) tma_wait_all();
-    if (TKEEP) tmem_free_cta<TKEEP ? C::TCOLS : 32>(tbase);
+    if (TKEEP) tmem_free_cta<TMEM_COLS>(tbase);
 }
 
 }  // namespace xfb

@@ -151,6 +151,11 @@ __device__ __forceinline__ void tmem_park(unsigned taddr, const cpx (&r)[16])
         "f"(r[14].y), "f"(r[15].x), "f"(r[15].y)
         : "memory");
 }
+// one complex register -> 2 columns
+__device__ __forceinline__ void tmem_park1(unsigned taddr, const cpx r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "f"(r.x), "f"(r.y) : "memory");
+}
 // 8 complex registers -> 16 columns
 __device__ __forceinline__ void tmem_park8(unsigned taddr, const cpx (&r)[8])
 {

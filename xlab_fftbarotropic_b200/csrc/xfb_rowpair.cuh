@@ -335,7 +335,11 @@ rowpair_jac_tmem_kernel(const RowParams p)
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = mk(v[q].x + __ldg(sa + t + q * G), v[q].y + __ldg(sb + t + q * G));
         }
-        r2c_pair<NY, false>(v, p.spec_out + po, p, alive ? p.pitch : 0, sm, t, tw, bar);
+        // the thread index is laundered per pair: otherwise the 24 padded shared-memory positions of the forward
+        // transform's tail are hoisted out of the pair loop and spilled (16 local loads per pair on the critical path)
+        int tl = t;
+        asm volatile("" : "+r"(tl));
+        r2c_pair<NY, false>(v, p.spec_out + po, p, alive ? p.pitch : 0, sm, tl, tw, bar);
     }
 #undef XFB_FETCH
 #undef XFB_PAIR_OF
