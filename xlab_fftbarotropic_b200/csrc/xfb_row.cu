@@ -60,11 +60,11 @@ static int launch_pair_t(const RowParams &p, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
-// ROW_JAC with the parked products in TENSOR MEMORY and double-buffered staging.  Default at NY = 8192, where the
-// shared-memory parks leave room for one staging buffer only (0.52 vs 0.58 ms per launch at 8192^2); at 4096 and below
-// two CTAs per SM already hide the fetches and the shared-memory parks are faster (4096^2: 0.136 vs 0.126 ms).
-// XFB_ROW_TMEM=0 / 1 forces either kernel (A/B knob).  The first version moved 32 registers per tcgen05.ld / st and
-// spilled 300 bytes per thread (0.62 ms); halves of 16 registers do not.
+// ROW_JAC with the parked products in TENSOR MEMORY and double-buffered staging.  Default at NY >= 4096 (per launch:
+// 8192^2 0.496 vs 0.58 ms, 4096^2 0.122 vs 0.126 ms); at 2048 and below several CTAs per SM already hide the fetches and
+// the shared-memory parks are faster (2048^2: 0.037 vs 0.042 ms).  XFB_ROW_TMEM=0 / 1 forces either kernel (A/B knob).
+// The first version moved 32 registers per tcgen05.ld / st and spilled 300 bytes per thread (0.62 ms at 8192^2); halves
+// of 16 registers, a laundered thread index and one flat loop over the fetches brought it to zero spills.
 template <int NY>
 static int launch_pair_tmem(const RowParams &p, cudaStream_t st)
 {
@@ -90,7 +90,7 @@ static int launch_pair_tmem(const RowParams &p, cudaStream_t st)
 static bool use_tmem_parks(int ny)
 {
     static const int forced = getenv("XFB_ROW_TMEM") ? (atoi(getenv("XFB_ROW_TMEM")) != 0 ? 1 : 0) : -1;
-    return forced >= 0 ? forced == 1 : ny == 8192;
+    return forced >= 0 ? forced == 1 : ny >= 4096;
 }
 
 // XFB_ROW_SINGLE=1 forces the one-row-per-line kernel (tuning / A-B knob); 16384 always uses it

@@ -265,60 +265,58 @@ rowpair_jac_tmem_kernel(const RowParams p)
     } while (0)
     XFB_FETCH(0);
     XFB_FETCH(1);
-    unsigned phase = 0;      // bit b: parity to wait for on buffer b
     cpx v[16];
-    int n = 0;
-    for (int gi = 0; gi < my_groups; ++gi) {
-        const int g = blockIdx.x + gi * gridDim.x;
-        const int pr = XFB_PAIR_OF(g);
-        const bool alive = g * C::PPC + lane_pair < npairs;
-        const size_t po = (size_t)pr * (size_t)(2 * p.pitch), ro = (size_t)pr * (size_t)(2 * NY);
+    // ONE flat loop over the fetches of this pair slot (field f = n & 3 of pair group n >> 2): the only loop-carried
+    // scalar is n -- staging buffer n & 1 is on its (n >> 1)-th use, so its mbarrier parity is (n >> 1) & 1, and the
+    // pair offsets are recomputed where they are needed instead of living (spilled) across the transforms.
 #pragma unroll 1
-        for (int f = 0; f < 4; ++f, ++n) {
+    for (int n = 0; n < nfetch; ++n) {
+        const int f = n & 3;
+        {
             const int b = n & 1;
-            mbar_wait(mbar + b, (phase >> b) & 1);
-            phase ^= 1u << b;
-            {
-                const float4 *st = reinterpret_cast<const float4 *>(stage0 + b * ST_STRIDE);
+            mbar_wait(mbar + b, (unsigned)(n >> 1) & 1u);
+            const float4 *st = reinterpret_cast<const float4 *>(stage0 + b * ST_STRIDE);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int pos = t + (8 * h + e) * G;
-                        const int m = (h == 0) ? pos : NY - pos;
-                        float4 x = st[m];
-                        if ((h == 0 && e == 0 && pos == 0) || (h == 1 && e == 0 && pos == NY / 2)) { x.y = 0.f; x.w = 0.f; }
-                        v[8 * h + e] = (h == 0) ? mk(x.y + x.z, x.x - x.w) : mk(x.z - x.y, x.x + x.w);
-                    }
-                }
-            }
-            bar.sync();                 // everyone has read this staging buffer: refill it two fields ahead
-            XFB_FETCH(n + 2);
-            line_fft<NY, 1>(v, sm, t, 0, tw, bar);
-            // v = (b[n], a[n]) unscaled, swapped: .y is row 2m, .x row 2m+1.  Tensor-memory traffic in halves of
-            // eight values (16 registers) so that nothing spills next to the live butterfly set.
-            if (f == 0 || f == 2) {
-                const unsigned park = (f == 0) ? park0 : park1;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    cpx a[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) a[q] = mk(v[8 * h + q].y * p.scale, v[8 * h + q].x * p.scale);      // -u ; v
-                    tmem_park8(park + 16 * h, a);
-                }
-            } else if (f == 1) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    cpx a[8];
-                    tmem_unpark8(park0 + 16 * h, a);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        a[q] = mk(a[q].x * (v[8 * h + q].y * p.scale), a[q].y * (v[8 * h + q].x * p.scale));           // -u dvortdx
-                    tmem_park8(park0 + 16 * h, a);
+                for (int e = 0; e < 8; ++e) {
+                    const int pos = t + (8 * h + e) * G;
+                    const int m = (h == 0) ? pos : NY - pos;
+                    float4 x = st[m];
+                    if ((h == 0 && e == 0 && pos == 0) || (h == 1 && e == 0 && pos == NY / 2)) { x.y = 0.f; x.w = 0.f; }
+                    v[8 * h + e] = (h == 0) ? mk(x.y + x.z, x.x - x.w) : mk(x.z - x.y, x.x + x.w);
                 }
             }
         }
-        // J = (-u dvortdx) - v dvortdy, formed in place in v                                       main.cpp:225-227
+        bar.sync();                 // everyone has read this staging buffer: refill it two fields ahead
+        XFB_FETCH(n + 2);
+        line_fft<NY, 1>(v, sm, t, 0, tw, bar);
+        // v = (b[n], a[n]) unscaled, swapped: .y is row 2m, .x row 2m+1.  Tensor-memory traffic in halves of
+        // eight values (16 registers) so that nothing spills next to the live butterfly set.
+        if (f == 0 || f == 2) {
+            const unsigned park = (f == 0) ? park0 : park1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                cpx a[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) a[q] = mk(v[8 * h + q].y * p.scale, v[8 * h + q].x * p.scale);      // -u ; v
+                tmem_park8(park + 16 * h, a);
+            }
+            continue;
+        }
+        if (f == 1) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                cpx a[8];
+                tmem_unpark8(park0 + 16 * h, a);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    a[q] = mk(a[q].x * (v[8 * h + q].y * p.scale), a[q].y * (v[8 * h + q].x * p.scale));           // -u dvortdx
+                tmem_park8(park0 + 16 * h, a);
+            }
+            continue;
+        }
+        // f == 3: J = (-u dvortdx) - v dvortdy, formed in place in v                             main.cpp:225-227
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             cpx a[8];
@@ -330,8 +328,11 @@ rowpair_jac_tmem_kernel(const RowParams p)
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[8 * h + q] = mk(a[q].x - v[8 * h + q].x, a[q].y - v[8 * h + q].y);
         }
+        const int g = (int)blockIdx.x + (n >> 2) * (int)gridDim.x;
+        const int pr = XFB_PAIR_OF(g);
+        const bool alive = g * C::PPC + lane_pair < npairs;
         if (p.real_in != nullptr) {
-            const float *sa = p.real_in + ro, *sb = sa + NY;
+            const float *sa = p.real_in + (size_t)pr * (size_t)(2 * NY), *sb = sa + NY;
 #pragma unroll
             for (int q = 0; q < 16; ++q) v[q] = mk(v[q].x + __ldg(sa + t + q * G), v[q].y + __ldg(sb + t + q * G));
         }
@@ -339,7 +340,7 @@ rowpair_jac_tmem_kernel(const RowParams p)
         // transform's tail are hoisted out of the pair loop and spilled (16 local loads per pair on the critical path)
         int tl = t;
         asm volatile("" : "+r"(tl));
-        r2c_pair<NY, false>(v, p.spec_out + po, p, alive ? p.pitch : 0, sm, tl, tw, bar);
+        r2c_pair<NY, false>(v, p.spec_out + (size_t)pr * (size_t)(2 * p.pitch), p, alive ? p.pitch : 0, sm, tl, tw, bar);
     }
 #undef XFB_FETCH
 #undef XFB_PAIR_OF
