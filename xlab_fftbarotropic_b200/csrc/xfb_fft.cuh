@@ -39,6 +39,11 @@ __device__ __forceinline__ cpx launder(cpx w)
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+// one instruction pulls a whole contiguous range towards L2 (16-byte aligned, size a multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *ptr, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
 
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) and their mbarrier --------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
