@@ -18,48 +18,69 @@ namespace xfb {
 // tw[k] = exp(-2 pi i k / n).  SIGN = +1: forward (e^{-i}), -1: inverse (e^{+i}), unnormalised.
 template <int SIGN>
 __device__ cpx *gen_fft(cpx *a, cpx *b, const int n, const int nl, const int *__restrict__ fac, const int nfac,
-                        const cpx *__restrict__ tw)
+                        const cpx *__restrict__ tw, const int tpl)
 {
+    // tpl threads work on one line (tpl divides blockDim.x): no per-butterfly integer division
+    const int line0 = threadIdx.x / tpl, lane = threadIdx.x - line0 * tpl, lpb = blockDim.x / tpl;
     int ns = 1;
     for (int f = 0; f < nfac; ++f) {
         const int r = fac[f], m = n / r;              // m butterflies per line
-        const int tstep = n / (ns * r);               // twiddle exp(-2 pi i s k / (ns r)) = tw[s * k * tstep]
-        for (int idx = threadIdx.x; idx < nl * m; idx += blockDim.x) {
-            const int line = idx / m, j = idx - line * m;
-            const int k = j % ns;
+        const int tstep = n / (ns * r);               // twiddle exp(-2 pi i s k / (ns r)) = tw[s * k * tstep], index < n
+        const bool pow2 = (ns & (ns - 1)) == 0;       // radices 4 and 2 come first: ns stays a power of two for them
+        for (int line = line0; line < nl; line += lpb) {
             const cpx *src = a + (size_t)line * n;
-            cpx *dst = b + (size_t)line * n + (j - k) * r + k;
-            cpx x[5];
-            for (int s = 0; s < r; ++s) {
-                cpx v = src[j + s * m];
-                if (s > 0 && k > 0) {
-                    cpx w = tw[(s * k * tstep) % n];
-                    if (SIGN < 0) w.y = -w.y;
-                    v = cmul(v, w);
-                }
-                x[s] = v;
-            }
-            if (r == 2) {
-                dst[0] = cadd(x[0], x[1]);
-                dst[ns] = csub(x[0], x[1]);
-            } else if (r == 4) {
-                const cpx t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]), t2 = cadd(x[1], x[3]);
-                cpx t3 = csub(x[1], x[3]);
-                t3 = (SIGN > 0) ? mul_negi(t3) : mul_i(t3);
-                dst[0] = cadd(t0, t2);
-                dst[ns] = cadd(t1, t3);
-                dst[2 * ns] = csub(t0, t2);
-                dst[3 * ns] = csub(t1, t3);
-            } else {
-                // direct DFT of length r = 3 or 5 with the table: W_r^{q s} = tw[(q s mod r) * n / r]
-                for (int q = 0; q < r; ++q) {
-                    cpx acc = x[0];
-                    for (int s = 1; s < r; ++s) {
-                        cpx w = tw[((q * s) % r) * (n / r)];
+            cpx *dl = b + (size_t)line * n;
+            for (int j = lane; j < m; j += tpl) {
+                const int k = pow2 ? (j & (ns - 1)) : (j % ns);
+                cpx *dst = dl + (j - k) * r + k;
+                cpx x[5];
+                x[0] = src[j];
+                for (int s = 1; s < r; ++s) {
+                    cpx v = src[j + s * m];
+                    if (k > 0) {
+                        cpx w = tw[s * k * tstep];
                         if (SIGN < 0) w.y = -w.y;
-                        acc = cadd(acc, cmul(x[s], w));
+                        v = cmul(v, w);
                     }
-                    dst[q * ns] = acc;
+                    x[s] = v;
+                }
+                if (r == 2) {
+                    dst[0] = cadd(x[0], x[1]);
+                    dst[ns] = csub(x[0], x[1]);
+                } else if (r == 4) {
+                    const cpx t0 = cadd(x[0], x[2]), t1 = csub(x[0], x[2]), t2 = cadd(x[1], x[3]);
+                    cpx t3 = csub(x[1], x[3]);
+                    t3 = (SIGN > 0) ? mul_negi(t3) : mul_i(t3);
+                    dst[0] = cadd(t0, t2);
+                    dst[ns] = cadd(t1, t3);
+                    dst[2 * ns] = csub(t0, t2);
+                    dst[3 * ns] = csub(t1, t3);
+                } else if (r == 3) {
+                    // y0 = x0 + x1 + x2 ; y1,2 = x0 - (x1 + x2)/2 -+ i (sqrt(3)/2)(x1 - x2)   (forward; inverse swaps)
+                    const cpx t1 = cadd(x[1], x[2]);
+                    const cpx t2 = mk(x[0].x - 0.5f * t1.x, x[0].y - 0.5f * t1.y);
+                    const cpx d = csub(x[1], x[2]);
+                    cpx t3 = mk(0.86602540378443864676f * d.x, 0.86602540378443864676f * d.y);
+                    t3 = (SIGN > 0) ? mul_negi(t3) : mul_i(t3);
+                    dst[0] = cadd(x[0], t1);
+                    dst[ns] = cadd(t2, t3);
+                    dst[2 * ns] = csub(t2, t3);
+                } else {
+                    // radix 5: c1 = cos(2 pi/5), c2 = cos(4 pi/5), s1 = sin(2 pi/5), s2 = sin(4 pi/5)
+                    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+                    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+                    const cpx a1 = cadd(x[1], x[4]), a2 = cadd(x[2], x[3]), b1 = csub(x[1], x[4]), b2 = csub(x[2], x[3]);
+                    const cpx p1 = mk(x[0].x + c1 * a1.x + c2 * a2.x, x[0].y + c1 * a1.y + c2 * a2.y);
+                    const cpx p2 = mk(x[0].x + c2 * a1.x + c1 * a2.x, x[0].y + c2 * a1.y + c1 * a2.y);
+                    cpx q1 = mk(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+                    cpx q2 = mk(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+                    q1 = (SIGN > 0) ? mul_negi(q1) : mul_i(q1);
+                    q2 = (SIGN > 0) ? mul_negi(q2) : mul_i(q2);
+                    dst[0] = mk(x[0].x + a1.x + a2.x, x[0].y + a1.y + a2.y);
+                    dst[ns] = cadd(p1, q1);
+                    dst[2 * ns] = cadd(p2, q2);
+                    dst[3 * ns] = csub(p2, q2);
+                    dst[4 * ns] = csub(p1, q1);
                 }
             }
         }
@@ -85,7 +106,7 @@ __global__ void gen_rows_r2c(const GenParams g, const float *__restrict__ in, cp
     const size_t row = blockIdx.x;
     for (int j = threadIdx.x; j < g.ny; j += blockDim.x) a[j] = mk(in[row * g.ny + j], 0.f);
     __syncthreads();
-    const cpx *r = gen_fft<1>(a, b, g.ny, 1, g.facy, g.nfy, g.twy);
+    const cpx *r = gen_fft<1>(a, b, g.ny, 1, g.facy, g.nfy, g.twy, blockDim.x);
     for (int j = threadIdx.x; j < g.hy; j += blockDim.x) out[row * g.hy + j] = r[j];
 }
 
@@ -102,7 +123,7 @@ __global__ void gen_rows_c2r(const GenParams g, const cpx *__restrict__ in, floa
         if (j > 0 && j < g.ny / 2) a[g.ny - j] = cconj(v);
     }
     __syncthreads();
-    const cpx *r = gen_fft<-1>(a, b, g.ny, 1, g.facy, g.nfy, g.twy);
+    const cpx *r = gen_fft<-1>(a, b, g.ny, 1, g.facy, g.nfy, g.twy, blockDim.x);
     for (int j = threadIdx.x; j < g.ny; j += blockDim.x) out[row * g.ny + j] = r[j].x * scale;
 }
 
@@ -119,7 +140,7 @@ __global__ void gen_cols(const GenParams g, const cpx *__restrict__ in, cpx *__r
         a[(size_t)c * g.nx + i] = in[(size_t)i * g.hy + j0 + c];
     }
     __syncthreads();
-    const cpx *r = gen_fft<SIGN>(a, b, g.nx, wl, g.facx, g.nfx, g.twx);
+    const cpx *r = gen_fft<SIGN>(a, b, g.nx, wl, g.facx, g.nfx, g.twx, blockDim.x / w);
     for (int idx = threadIdx.x; idx < g.nx * wl; idx += blockDim.x) {
         const int i = idx / wl, c = idx - i * wl;
         out[(size_t)i * g.hy + j0 + c] = r[(size_t)c * g.nx + i];
@@ -172,7 +193,7 @@ __global__ void gen_stage(const cpx *T, cpx *z0, cpx *zk, cpx *acc, const int nx
 struct GenericPlan {
     GenParams g;
     cpx *twx, *twy;
-    int cols_w;
+    int cols_w, row_threads;
     size_t smem_rows, smem_cols;
 };
 
@@ -215,9 +236,12 @@ int generic_create(xfb_handle h)
     if (make_table(&P->twx, h->nx) || make_table(&P->twy, h->ny)) return XFB_E_CUDA;
     P->g.twx = P->twx; P->g.twy = P->twy;
     P->smem_rows = 2 * sizeof(cpx) * h->ny;
+    // column tile width: 4 columns (32-byte rows) unless that leaves fewer than two CTAs per SM -- these grids live in
+    // L2, parallelism matters more than sector efficiency; always a power of two so that it divides the block size
     int w = 4;
-    while (w > 1 && 2 * sizeof(cpx) * (size_t)w * h->nx > 200 * 1024) --w;
+    while (w > 1 && (2 * sizeof(cpx) * (size_t)w * h->nx > 100 * 1024 || (h->hy + w - 1) / w < 2 * 148)) w /= 2;
     P->cols_w = w;
+    P->row_threads = (h->ny >= 512) ? 256 : 128;
     P->smem_cols = 2 * sizeof(cpx) * (size_t)w * h->nx;
     CK(cudaFuncSetAttribute(gen_rows_r2c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_rows));
     CK(cudaFuncSetAttribute(gen_rows_c2r, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_rows));
@@ -249,7 +273,7 @@ int generic_fwd2d(xfb_handle h, const float *real_in, cpx *tmp, cpx *spec_out)
 {
     GenericPlan *P = (GenericPlan *)h->generic;
     const int tiles = (h->hy + P->cols_w - 1) / P->cols_w;
-    GLAUNCH(h, (gen_rows_r2c<<<h->nx, 128, P->smem_rows, h->stream>>>(P->g, real_in, tmp)));
+    GLAUNCH(h, (gen_rows_r2c<<<h->nx, P->row_threads, P->smem_rows, h->stream>>>(P->g, real_in, tmp)));
     GLAUNCH(h, (gen_cols<1><<<tiles, 256, P->smem_cols, h->stream>>>(P->g, tmp, spec_out, P->cols_w)));
     return 0;
 }
@@ -259,7 +283,7 @@ int generic_inv2d(xfb_handle h, const cpx *spec_in, cpx *tmp, float *real_out, f
     GenericPlan *P = (GenericPlan *)h->generic;
     const int tiles = (h->hy + P->cols_w - 1) / P->cols_w;
     GLAUNCH(h, (gen_cols<-1><<<tiles, 256, P->smem_cols, h->stream>>>(P->g, spec_in, tmp, P->cols_w)));
-    GLAUNCH(h, (gen_rows_c2r<<<h->nx, 128, P->smem_rows, h->stream>>>(P->g, tmp, real_out, negate ? -scale : scale)));
+    GLAUNCH(h, (gen_rows_c2r<<<h->nx, P->row_threads, P->smem_rows, h->stream>>>(P->g, tmp, real_out, negate ? -scale : scale)));
     return 0;
 }
 
