@@ -309,7 +309,7 @@ int xfb::destroy_impl(xfb_handle h)
         cudaStreamDestroy(h->rec_stream);
     }
     void *ptrs[] = {h->tw, h->kx, h->ky, h->kx2, h->ky2, h->z0, h->zk, h->acc, h->jint, h->t_block, h->src, h->dg, h->real_a,
-                    h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b, h->recv_block, h->sync_buf, h->c0, h->ck, h->cacc, h->cjint, h->tc[0]};
+                    h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b, h->recv_block, h->sync_buf, h->c0, h->ck, h->cacc, h->cjint, h->tc[0], h->panel_base};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto pool : {h->ev_row, h->ev_col, h->ev_a2a})

@@ -92,6 +92,24 @@ static inline size_t col_off(xfb_handle h, int q, int c, int r0) { return ((size
 
 enum { ROW2COL = 0, COL2ROW = 1 };
 
+// Fused row -> column exchange (XFB_SLAB_FUSED=0 turns it off): K-ROW stores its output panels straight into the
+// receive arrays of the ranks that own the columns -- plain 16-byte stores on the CUDA-IPC peer mappings, NVLink traffic
+// issued by the transform kernel itself while it computes -- instead of writing them locally and having a push kernel
+// or the copy engines move them afterwards.  recv_of_rank[q] = receive block of rank q as seen from this process
+// (array 0 of the block = jint_recv).  Panel (q, c) of rank `me` lands at rows [me * rows, ...) of chunk c there.
+static int build_panel_table(xfb_handle h, cpx *const *recv_of_rank)
+{
+    static const bool off = getenv("XFB_SLAB_FUSED") && atoi(getenv("XFB_SLAB_FUSED")) == 0;
+    if (off) return 0;
+    const int n = h->nranks * h->nchunks;
+    std::vector<cpx *> tab(n);
+    for (int q = 0; q < h->nranks; ++q)
+        for (int c = 0; c < h->nchunks; ++c) tab[q * h->nchunks + c] = recv_of_rank[q] + col_off(h, h->rank, c, 0);
+    if (dev_alloc((void **)&h->panel_base, sizeof(cpx *) * n)) return XFB_E_CUDA;
+    CK(cudaMemcpy(h->panel_base, tab.data(), sizeof(cpx *) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
 // ---- SM-driven push: one launch copies up to 64 contiguous segments into peer memory with 16-byte stores ------------
 // The copy engines lose more than half of their NVLink bandwidth while the SMs keep the memory system busy
 // (tools/probes/probe_p2p_copy.cu and the slab runs: 760 -> ~300 GB/s).  A few CTAs of plain ld.global / st.global on
@@ -261,11 +279,12 @@ static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *
 
 // ---- per-rank launches --------------------------------------------------------------------------------
 static int launch_row_chunk(xfb_handle h, int mode, const cpx *const in[4], const float *real_in, cpx *spec_out, float *real_out,
-                            int negate, int r0, int r1)
+                            int negate, int r0, int r1, bool fused_out = false)
 {
     RowParams r;
     fill_row(h, r, r1 - r0);
     const size_t so = (size_t)r0 * h->pitch, ro = (size_t)r0 * h->ny;
+    if (fused_out && h->panel_base) { r.panel_base = h->panel_base; r.out_row_off = (long long)so; }
     for (int f = 0; f < 4; ++f) r.spec_in[f] = in && in[f] ? in[f] + so : nullptr;
     r.real_in = real_in ? real_in + ro : nullptr;
     r.spec_out = spec_out ? spec_out + so : nullptr;
@@ -317,6 +336,18 @@ static int rows_then_exchange(Team *T, F produce, GR row_of, GC col_of)
     const int C = h0->nchunks, rc = h0->rows / C;
     cpx *rp[16], *cp[16];
     for (int l = 0; l < T->nlocal; ++l) { rp[l] = row_of(T->local[l]); cp[l] = col_of(T->local[l]); }
+    if (h0->panel_base) {
+        // fused exchange: the kernels have written into the receive arrays themselves; what is left is the barrier
+        for (int l = 0; l < T->nlocal; ++l)
+            if (int e = produce(T->local[l], 0, h0->rows)) return e;
+        if (T->loopback) return 0;
+        CK(cudaEventRecord(h0->ev_chunk[0], h0->stream));
+        CK(cudaStreamWaitEvent(h0->comm_stream, h0->ev_chunk[0], 0));
+        if (int e = phase_barrier(T, h0->comm_stream)) return e;
+        CK(cudaEventRecord(h0->ev_comm[0], h0->comm_stream));
+        CK(cudaStreamWaitEvent(h0->stream, h0->ev_comm[0], 0));
+        return 0;
+    }
     if (T->loopback) {
         for (int l = 0; l < T->nlocal; ++l)
             for (int i = 0; i < C; ++i)
@@ -376,7 +407,7 @@ static int team_set_vorticity(Team *T, const float *const *vort)
         [&](xfb_handle h, int r0, int r1) {
             int l = 0;
             while (T->local[l] != h) ++l;
-            return launch_row_chunk(h, ROW_R2C, nullptr, vort[l], h->jint, nullptr, 0, r0, r1);
+            return launch_row_chunk(h, ROW_R2C, nullptr, vort[l], h->jint, nullptr, 0, r0, r1, true);
         },
         [](xfb_handle h) { return h->jint; }, [](xfb_handle h) { return h->jint_recv; });
     if (e) return e;
@@ -410,7 +441,7 @@ static int team_step(Team *T, int nsteps, float dt)
             int e = rows_then_exchange(
                 T,
                 [&](xfb_handle h, int r0, int r1) {
-                    return launch_row_chunk(h, ROW_JAC, h->tr, h->has_src ? h->src : nullptr, h->jint, nullptr, 0, r0, r1);
+                    return launch_row_chunk(h, ROW_JAC, h->tr, h->has_src ? h->src : nullptr, h->jint, nullptr, 0, r0, r1, true);
                 },
                 [](xfb_handle h) { return h->jint; }, [](xfb_handle h) { return h->jint_recv; });
             if (e) return e;
@@ -622,6 +653,8 @@ extern "C" int xfb_create_dist(xfb_handle *out, int nx, int ny, float lx, float 
         if (const char *pb = getenv("XFB_SLAB_PUSH_BLOCKS")) h->push_blocks = atoi(pb) < 1 ? 1 : atoi(pb);
         cudaMemsetAsync(h->sync_buf, 0, sizeof(float), h->comm_stream);
         cudaStreamSynchronize(h->comm_stream);
+        if (h->p2p)
+            if (int e = build_panel_table(h, h->peer_recv)) return e;
     }
     return 0;
 }
@@ -680,6 +713,12 @@ extern "C" int xfb_loopback_create(xfb_loopback_s **out, int nx, int ny, float l
         }
         h->team = &L->team;
         L->team.local[r] = h;
+    }
+    {
+        cpx *recv[16];
+        for (int r = 0; r < nranks; ++r) recv[r] = L->team.local[r]->recv_block;
+        for (int r = 0; r < nranks; ++r)
+            if (int e = build_panel_table(L->team.local[r], recv)) return e;
     }
     if (dev_alloc((void **)&L->full, sizeof(float) * (size_t)nx * ny)) return XFB_E_CUDA;
     *out = L;

@@ -83,6 +83,8 @@ struct xfb_handle_s {
     bool p2p;                       // exchange by pushes into peer_recv (else ncclSend/ncclRecv)
     bool push_sm;                   // p2p: pushes by an SM kernel (plain stores on the peer mappings) instead of the copy engines
     int push_blocks;                // CTAs per segment of the push kernel
+    xfb::cpx **panel_base;          // fused row->column exchange: device table [nranks * nchunks] of the places in the ranks'
+                                    // receive arrays where K-ROW writes its output panels directly (null: exchange by pushes)
     cudaStream_t comm_stream;
     cudaStream_t copy_stream[4];    // p2p transport: the pushes of one exchange are spread over several copy engines
     cudaEvent_t ev_copy[4], ev_fork;

@@ -40,6 +40,11 @@ struct RowParams {
     int cw;                  // columns per panel
     long long panel_stride;  // complex elements between panels (= local rows * cw)
     unsigned cw_magic;       // ceil(2^32 / cw): k / cw == __umulhi(k, cw_magic) for every k < pitch (checked on the host)
+    // DIST, fused exchange: panel (q, c) of the OUTPUT is not written to the local array but straight into the
+    // receive array of rank q (peer memory over NVLink, or the rank's own for q == me): panel_base[q * nchunks + c]
+    // points at rows [me * rows, ...) of chunk c there, out_row_off = first local row of this launch * cw.
+    cpx *const *panel_base;  // device array, null: local output
+    long long out_row_off;
     float scale;             // 1/(NX*NY) applied after every C2R (fftwf_backward_normalize)
     int negate;              // C2R: multiply by -1 after scaling (u = -u)
 };
@@ -80,6 +85,18 @@ __device__ __forceinline__ long long line_pos(const RowParams &p, const int k)
     if (!DIST) return 2 * k;
     const int panel = (int)__umulhi((unsigned)k, p.cw_magic);
     return (long long)panel * p.panel_stride + 2 * (k - panel * p.cw);
+}
+
+// address of output element k of the line whose local base pointer is `line` (= p.spec_out + line offset)
+template <bool DIST>
+__device__ __forceinline__ cpx *out_addr(const RowParams &p, cpx *line, const int k)
+{
+    if (!DIST) return line + 2 * k;
+    const int panel = (int)__umulhi((unsigned)k, p.cw_magic);
+    const long long within = 2 * (k - panel * p.cw);
+    if (p.panel_base == nullptr) return line + (long long)panel * p.panel_stride + within;
+    cpx *base = reinterpret_cast<cpx *>(__ldg(reinterpret_cast<const unsigned long long *>(p.panel_base) + panel));
+    return base + p.out_row_off + (line - p.spec_out) + within;
 }
 
 // base of the line of `row` in a pair-layout array whose rows hold `rowpitch` complex elements
@@ -154,10 +171,10 @@ __device__ __forceinline__ void r2c_line(cpx (&v)[16], cpx *__restrict__ Xout, c
         const cpx D = mk(0.5f * (Zk.x - Zm.x), 0.5f * (Zk.y - Zm.y));
         const cpx wk = (q == 0) ? wt : cmul(wt, w32(q));           // exp(-2 pi i k / NY)
         const cpx O = cmul(mul_negi(D), wk);
-        Xout[line_pos<DIST>(p, k)] = cadd(E, O);
-        if (k == 0) Xout[line_pos<DIST>(p, L)] = mk(Zk.x - Zk.y, 0.f);
+        *out_addr<DIST>(p, Xout, k) = cadd(E, O);
+        if (k == 0) *out_addr<DIST>(p, Xout, L) = mk(Zk.x - Zk.y, 0.f);
     }
-    for (int k = L + 1 + t; k < pitch; k += G) Xout[line_pos<DIST>(p, k)] = mk(0.f, 0.f);
+    for (int k = L + 1 + t; k < pitch; k += G) *out_addr<DIST>(p, Xout, k) = mk(0.f, 0.f);
 }
 
 template <int NY, int MODE, bool DIST>

@@ -103,12 +103,12 @@ __device__ __forceinline__ void r2c_pair(cpx (&v)[16], cpx *__restrict__ PBout, 
         o.y = 0.5f * (Z.y - M.y);
         o.z = 0.5f * (Z.y + M.y);                               // B = (Z - conj M) / (2i)
         o.w = 0.5f * (M.x - Z.x);
-        *reinterpret_cast<float4 *>(PBout + line_pos<DIST>(p, n)) = o;
+        *reinterpret_cast<float4 *>(out_addr<DIST>(p, PBout, n)) = o;
     }
     if (t == 0)                                                 // Nyquist bin: Z[NY/2] is its own mirror
-        *reinterpret_cast<float4 *>(PBout + line_pos<DIST>(p, NY / 2)) = make_float4(v[8].x, 0.f, v[8].y, 0.f);
+        *reinterpret_cast<float4 *>(out_addr<DIST>(p, PBout, NY / 2)) = make_float4(v[8].x, 0.f, v[8].y, 0.f);
     for (int k = NY / 2 + 1 + t; k < pitch; k += G)
-        *reinterpret_cast<float4 *>(PBout + line_pos<DIST>(p, k)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4 *>(out_addr<DIST>(p, PBout, k)) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // forward transform in two halves so a bulk fetch can be issued between the transform and the stores:
@@ -145,11 +145,11 @@ __device__ __forceinline__ void r2c_pair_finish(const cpx (&v)[16], cpx *__restr
         o.y = 0.5f * (Z.y - M.y);
         o.z = 0.5f * (Z.y + M.y);
         o.w = 0.5f * (M.x - Z.x);
-        *reinterpret_cast<float4 *>(PBout + line_pos<DIST>(p, n)) = o;
+        *reinterpret_cast<float4 *>(out_addr<DIST>(p, PBout, n)) = o;
     }
-    if (t == 0) *reinterpret_cast<float4 *>(PBout + line_pos<DIST>(p, NY / 2)) = make_float4(v[8].x, 0.f, v[8].y, 0.f);
+    if (t == 0) *reinterpret_cast<float4 *>(out_addr<DIST>(p, PBout, NY / 2)) = make_float4(v[8].x, 0.f, v[8].y, 0.f);
     for (int k = NY / 2 + 1 + t; k < pitch; k += G)
-        *reinterpret_cast<float4 *>(PBout + line_pos<DIST>(p, k)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4 *>(out_addr<DIST>(p, PBout, k)) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // JAC with plain vector loads (slab runs: a line is cut into panels, not one contiguous region)
