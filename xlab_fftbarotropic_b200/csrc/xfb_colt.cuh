@@ -13,7 +13,12 @@
 //     two-column tile is transformed one column after the other (FW = 1): one butterfly per thread per pass
 //     (no register spills), at the access granularity of two columns.
 //   * CTAs are persistent (one per SM) and walk over tiles.
-// State arrays z0 / zk / acc are tile-major with tile width FW (one column group = one contiguous block).
+//   * NX = 8192 (one staging buffer only) uses TENSOR MEMORY for what shared memory and registers cannot hold:
+//     the new stage state of both columns between the epilogue and the four products (TKEEP), and the NEXT tile,
+//     streamed in through a three-slot ring of TMA boxes while the current tile's inverse transforms run (ColtRing,
+//     hooked into col_fft between its exchanges).  All 512 TMEM columns of the SM are allocated by the CTA.
+// State arrays z0 / zk / acc are tile-major with tile width FW (one column group = one contiguous block); a tile's
+// blocks are pulled towards L2 with cp.async.bulk.prefetch.L2 at tile start.
 #pragma once
 #include <cuda.h>
 
