@@ -99,6 +99,33 @@ def _slab_worker(rank, world, port, n, C, out):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("n,P,C", [(64, 2, 1), (128, 4, 2), (256, 8, 4)])
+def test_fused_panel_table_is_the_transpose(n, P, C):
+    """Fused row -> column exchange (csrc/xfb_dist.cu build_panel_table, xfb_row.cuh out_addr): every rank stores
+    output element (local row r, global column k) at  panel_base[k // cw] + r * cw + k % cw  with
+    panel_base[q * C + c] = receive array of rank q + col_off(me, c, 0).  A numpy model of exactly that addressing
+    must give every rank the x-transformable chunks [n][cw] of numpy's rfft2."""
+    import xlab_fftbarotropic_b200 as xfb
+    parts = [xfb.slab_partition(n, n, P, C, r) for r in range(P)]
+    rows, cw, pg = parts[0]["rows"], parts[0]["chunk_cols"], parts[0]["pitch_global"]
+    full = fields.elliptic(n).astype(np.float64)
+    recv = [np.zeros(C * n * cw, np.complex128) for _ in range(P)]          # jint_recv of every rank
+    for me in range(P):
+        y = np.zeros((rows, pg), np.complex128)
+        y[:, :n // 2 + 1] = np.fft.rfft(full[parts[me]["row0"]:parts[me]["row0"] + rows], axis=1)
+        table = [(q, _col_off(me, c, 0, C, rows, cw, n)) for q in range(P) for c in range(C)]   # panel -> (rank, offset)
+        for r in range(rows):
+            for panel in range(P * C):
+                q, base = table[panel]
+                recv[q][base + r * cw:base + (r + 1) * cw] = y[r, panel * cw:(panel + 1) * cw]
+    ref = np.zeros((n, pg), np.complex128)
+    ref[:, :n // 2 + 1] = np.fft.rfft2(full)
+    for q in range(P):
+        spec = np.concatenate([np.fft.fft(recv[q][c * n * cw:(c + 1) * n * cw].reshape(n, cw), axis=0) for c in range(C)], axis=1)
+        err = np.abs(spec - ref[:, parts[q]["col0"]:parts[q]["col0"] + C * cw]).max() / np.abs(ref).max()
+        assert err < 1e-12, (q, err)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
