@@ -144,6 +144,9 @@ int xfb_create_dist(xfb_handle *h, int nx, int ny, float lx, float ly, float nu,
 /* transport of a slab handle: 0 none (one rank), 1 grouped ncclSend/ncclRecv (XFB_SLAB_NCCL=1), 2 copy-engine
  * pushes / 3 SM push kernel into the peers' receive arrays mapped over CUDA IPC (XFB_SLAB_PUSH=ce|sm) */
 int xfb_slab_transport(xfb_handle h);
+/* 1 if K-ROW stores its output panels straight into the peers' receive arrays (fused row -> column transpose; P2P
+ * transports only, XFB_SLAB_FUSED=0 turns it off), else 0 */
+int xfb_slab_fused(xfb_handle h);
 /* summed milliseconds of the all-to-all exchanges since xfb_profile(h, 1) (NCCL handles) */
 int xfb_profile_read_a2a(xfb_handle h, double *a2a_ms, long long *exchanges);
 /* loopback team: all ranks of a slab decomposition in ONE process on ONE device, exchanging by

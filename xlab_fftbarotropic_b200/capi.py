@@ -23,7 +23,7 @@ SYMBOLS = [
     "xfb_set_tracer", "xfb_get_tracer_keff_hist",
     "xfb_host_alloc", "xfb_host_free", "xfb_get_field_async", "xfb_wait_field",
     "xfb_invert_pres", "xfb_launch_count", "xfb_stream", "xfb_size_supported", "xfb_profile", "xfb_profile_read",
-    "xfb_slab_partition", "xfb_nccl_unique_id", "xfb_create_dist", "xfb_profile_read_a2a", "xfb_slab_transport",
+    "xfb_slab_partition", "xfb_nccl_unique_id", "xfb_create_dist", "xfb_profile_read_a2a", "xfb_slab_transport", "xfb_slab_fused",
     "xfb_loopback_create", "xfb_loopback_destroy", "xfb_loopback_set_vorticity", "xfb_loopback_set_source",
     "xfb_loopback_step", "xfb_loopback_get_field", "xfb_loopback_launch_count",
 ]
@@ -80,6 +80,7 @@ def load():
     L.xfb_create_dist.argtypes = [C.POINTER(vp), ci, ci, cf, cf, cf, ci, ci, ci, ci, C.c_char_p]
     L.xfb_profile_read_a2a.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.xfb_slab_transport.argtypes = [vp]
+    L.xfb_slab_fused.argtypes = [vp]
     L.xfb_loopback_create.argtypes = [C.POINTER(vp), ci, ci, cf, cf, cf, ci, ci, ci]
     L.xfb_loopback_destroy.argtypes = [vp]
     L.xfb_loopback_set_vorticity.argtypes = [vp, vp]
@@ -300,7 +301,10 @@ class SlabBackend(Backend):
 
     @property
     def transport(self):
-        return {0: "none", 1: "nccl send/recv", 2: "p2p copy engines (CUDA IPC)", 3: "p2p SM push kernel (CUDA IPC)"}[int(self._L.xfb_slab_transport(self._h))]
+        t = {0: "none", 1: "nccl send/recv", 2: "p2p copy engines (CUDA IPC)", 3: "p2p SM push kernel (CUDA IPC)"}[int(self._L.xfb_slab_transport(self._h))]
+        if int(self._L.xfb_slab_fused(self._h)):
+            t += " for column->row, row->column fused into K-ROW (stores into peer memory)"
+        return t
 
     def a2a_read(self):
         ms, n = C.c_double(), C.c_longlong()

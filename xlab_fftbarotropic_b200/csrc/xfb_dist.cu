@@ -665,6 +665,8 @@ extern "C" int xfb_slab_transport(xfb_handle h)
     return h->p2p ? (h->push_sm ? 3 : 2) : 1;   // 3: SM push kernel, 2: copy-engine pushes (both over CUDA IPC peer mappings), 1: ncclSend/ncclRecv
 }
 
+extern "C" int xfb_slab_fused(xfb_handle h) { return (h && h->nranks > 1 && h->panel_base) ? 1 : 0; }
+
 extern "C" int xfb_profile_read_a2a(xfb_handle h, double *a2a_ms, long long *exchanges)
 {
     if (!h || !a2a_ms || !exchanges) return fail(XFB_E_ARG, "null argument");
