@@ -1,13 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- RK4 grid-point.steps/s of the pseudospectral barotropic step on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--grid 8192] [--impl xfb|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--grid G] [--impl xfb|reference]
 
-One "step" is one RK4 step (4 tendency evaluations = 20 2-D FFTs in the reference) of the elliptic
-vortex (reference generator makefield-elliptic-vortex.cpp) on a GRID x GRID doubly periodic domain.
-N > 1 (launched by torchrun, one rank per GPU): independent ensemble members, one per GPU, no
-data-path communication ("scaling": "weak"); the slab-decomposed single-field path is reported by
-the slab bench.
+One "step" is one RK4 step (4 tendency evaluations = 20 2-D FFTs in the reference).
+  N = 1 : the elliptic vortex (reference generator makefield-elliptic-vortex.cpp) at 8192^2 -- the headline grid of
+          BASELINE.json's north_star -- on one GPU ("scaling": "weak").
+  N > 1 (launched by torchrun, one rank per GPU): BASELINE.json configs[4], the 16384^2 constant vortex SLAB-DECOMPOSED
+          over the N GPUs with an NVLink all-to-all per 2-D transform ("scaling": "strong": the grid is fixed).  The
+          same run verifies the slab result against the single-GPU path on that grid, measures the single-GPU time
+          per step (T1) for parallel_efficiency = T1 / (N * T_N), and reports independent ensemble members (one
+          8192^2 member per GPU, no communication) as the sub-record "ensemble".  `--ensemble` makes the ensemble the
+          headline instead (the round-1 behaviour).
 
 Output: ONE JSON line on rank 0 (keys documented in DESIGN.md "Measurement").
 """
@@ -130,21 +134,27 @@ def physical_gpu_index(local_rank: int) -> int:
 # CPU reference leg (oracle/_ref = the unmodified reference main.cpp built against the FFT shim)
 # --------------------------------------------------------------------------------------------------
 
-def run_reference_steps(n: int, dt: float, steps_a: int, steps_b: int, threads: int):
+def run_reference_steps(n: int, dt: float, steps_a: int, steps_b: int, threads: int, field: str = "elliptic", budget_s: float = None):
     """Times the UNMODIFIED reference binary for two run lengths and differences them
-    (start-up, table build and the step-0 record dump cancel).  Returns seconds per step."""
+    (start-up, table build and the step-0 record dump cancel).  Returns seconds per step.
+    budget_s: the second run length is cut so that the whole measurement stays within about that many seconds
+    (estimated from the first run); the run lengths actually used are returned in the note."""
     from oracle import build_oracle
     import fields
     exe = build_oracle.build_reference(n, programs=("main",)).get("main")
     if exe is None:
         return None, "no prebuilt reference binary for this grid"
-    v0 = fields.elliptic(n)
+    v0 = fields.GENERATORS[field](n)
     times = []
     with tempfile.TemporaryDirectory() as d:
         os.makedirs(os.path.join(d, "input"))
         os.makedirs(os.path.join(d, "output"))
         v0.tofile(os.path.join(d, "input", "initial_vorticity.bin"))
-        for steps in (steps_a, steps_b):
+        for k, steps in enumerate((steps_a, steps_b)):
+            if k == 1 and budget_s is not None:
+                # T(steps_a) = start-up + steps_a steps >= steps_a steps: a safe (over-)estimate of the step time
+                est = max(times[0] / max(1, steps_a), 1e-3)
+                steps = steps_b = max(steps_a + 2, min(steps_b, steps_a + int(budget_s / est)))
             env = dict(os.environ, XFB_SHIM_THREADS=str(threads), XFB_DT=repr(float(dt)),
                        XFB_TOTAL_STEPS=str(steps), XFB_RECORD_STEP=str(10 ** 9))
             t0 = time.perf_counter()
@@ -153,43 +163,70 @@ def run_reference_steps(n: int, dt: float, steps_a: int, steps_b: int, threads: 
     per_step = (times[1] - times[0]) / (steps_b - steps_a)
     if per_step <= 0:          # tiny samples: start-up noise larger than the steps themselves; fall back to the long run alone
         per_step = times[1] / steps_b
-    return per_step, None
+    return per_step, f"(T({steps_b} steps) - T({steps_a} steps)) / {steps_b - steps_a}"
+
+
+def single_thread_figure(n: int = 1024, nsteps: int = 4):
+    """the reference exactly as shipped (FFTW_ESTIMATE, no threads: main.cpp:126-135) -- one host thread, small grid"""
+    sec, how = run_reference_steps(n, dt_for(n), 1, 1 + nsteps, 1)
+    if sec is None or sec <= 0:
+        return None
+    return {"value": n * n / sec, "unit": UNIT, "cores": 1, "sample": f"elliptic {n}^2, 1 thread (as the reference ships), {how}"}
 
 
 def cpu_baseline(sample_n: int, nsteps: int):
     threads = os.cpu_count() or 1
-    sec, err = run_reference_steps(sample_n, dt_for(sample_n), 1, 1 + nsteps, threads)
+    sec, how = run_reference_steps(sample_n, dt_for(sample_n), 1, 1 + nsteps, threads, budget_s=25.0)
     if sec is None or sec <= 0:
-        return {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": err or "failed"}
+        return {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": how or "failed"}
     return {
         "value": sample_n * sample_n / sec, "unit": UNIT, "cores": threads, "kind": "reference",
         "sample": (f"unmodified reference main.cpp + fftw3f-equivalent shim (FFT rows/columns on {threads} OpenMP "
-                   f"threads, pointwise loops single-threaded as in the reference), elliptic {sample_n}^2, "
-                   f"(T({1 + nsteps} steps) - T(1 step))/{nsteps}"),
+                   f"threads, pointwise loops single-threaded as in the reference), elliptic {sample_n}^2, {how}"),
+        "single_thread": single_thread_figure(),
     }
 
 
 def reference_arm(args):
-    """--impl reference: the reference's CPU path on this box's host cores, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path (unmodified main.cpp + FFT shim) on this box's
+    host cores, ON THE PRODUCT ARM'S CONFIG: elliptic 8192^2 at N = 1, constant vortex 16384^2 at N > 1 (the reference has
+    no parallel path: the same single process whatever N).  Run-length differencing; the second
+    run length is bounded so the arm ends within a few minutes whatever K is."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_n = args.ref_grid
+    slab = args.gpus > 1 and not args.ensemble
+    field = "const" if slab else "elliptic"
+    grid = args.ref_grid or args.grid
     threads = os.cpu_count() or 1
-    sec, err = run_reference_steps(sample_n, dt_for(sample_n), max(1, args.warmup), max(1, args.warmup) + args.steps, threads)
+    import psutil
+    need = 26 * 4 * grid * grid            # 8 real + 11 complex arrays + 3 tables (main.cpp:103-123, fftwfop.cpp:5-79)
+    note = ""
+    while grid > 1024 and psutil.virtual_memory().available < 1.5 * need:
+        grid //= 2
+        need //= 4
+        note = f" (host memory too small for {args.grid}^2: sample at {grid}^2)"
+    dt = 3.0 if field == "const" else dt_for(grid)
+    wa = 1
+    sec, how = run_reference_steps(grid, dt, wa, wa + args.steps, threads, field=field, budget_s=args.ref_budget)
+    if sec is None and grid != 2048:
+        grid, note = 2048, f" (no reference binary for {args.grid}^2 here: sample at 2048^2)"
+        sec, how = run_reference_steps(grid, dt_for(grid) if field != "const" else 3.0, wa, wa + args.steps, threads, field=field,
+                                       budget_s=args.ref_budget)
     if sec is None:
-        print(json.dumps({"impl": "reference", "unavailable": err}))
+        print(json.dumps({"impl": "reference", "unavailable": how}))
         return
-    val = sample_n * sample_n / sec
-    sample = (f"unmodified reference main.cpp (oracle/_ref) + fftw3f-equivalent shim, {threads} OpenMP threads in the "
-              f"FFTs, each step = one RK4 step of the elliptic vortex at {sample_n}^2 (bounded sample of the "
-              f"{args.grid}^2 workload), T({args.warmup}+{args.steps}) - T({args.warmup}) differenced")
+    val = grid * grid / sec
+    sample = (f"unmodified reference main.cpp (oracle/_ref) + fftw3f-equivalent shim, {threads} OpenMP threads in the FFTs "
+              f"(pointwise loops single-threaded as in the reference), one RK4 step of the {field} vortex at {grid}^2{note}, {how}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong" if slab else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"elliptic vortex {args.grid}^2 RK4 (reference arm sample {sample_n}^2)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "config": {"workload": f"{field} vortex {args.grid}^2 RK4 step" + (f", reference arm sample {grid}^2" if grid != args.grid else ""),
+                   "grid": grid, "same_grid_as_product_arm": grid == args.grid},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
+                         "single_thread": single_thread_figure()},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -376,7 +413,7 @@ def gpu_arm(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.ref_grid, args.cpu_steps)
+        cpu = cpu_baseline(args.cpu_grid, args.cpu_steps)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -409,12 +446,13 @@ def gpu_arm(args):
 
 
 def slab_arm(args):
-    """--slab: ONE grid slab-decomposed over the GPUs (one rank per GPU, NVLink all-to-all per 2-D transform);
+    """N > 1 (or --slab): ONE grid slab-decomposed over the GPUs (one rank per GPU, NVLink all-to-all per 2-D transform);
     strong scaling.  Same JSON contract; the work is tools/slab_bench.py."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import slab_bench
-    a = argparse.Namespace(grid=args.grid, steps=args.steps, warmup=args.warmup, chunks=args.chunks, check=args.slab_check,
-                           field="const" if args.grid >= 16384 else "elliptic", e2e_steps=max(1, min(args.e2e_steps, 3)))
+    a = argparse.Namespace(grid=args.grid, steps=args.steps, warmup=args.warmup, chunks=args.chunks, no_check=args.no_slab_check,
+                           no_ensemble=args.no_ensemble_record, field="const" if args.grid >= 16384 else "elliptic",
+                           e2e_steps=max(1, min(args.e2e_steps, 3)))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
@@ -431,16 +469,22 @@ def slab_arm(args):
         "config": {"workload": f"{r['field']} vortex {args.grid}^2 RK4 step slab-decomposed over {world} GPU(s), dt={r['dt']:g}s, "
                                f"{args.chunks} chunks, transport {r['transport']}",
                    "grid": args.grid, "l2": "per-rank working set is larger than the 126 MB L2", "state_finite": r["state_finite"],
-                   "check_vs_single_gpu": r.get("check")},
+                   "check_vs_single_gpu": r.get("check"), "limiter": r["limiter"]},
         "clocks": clocks, "gpu_launches": r["gpu_launches_per_rank"] * world,
         "e2e": {k: r["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "steps", "ms_per_step")},
         "roofline": {"bound": "hbm", "achieved": ALGO_BYTES_PER_PT_STEP * r["value"] / world / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": ALGO_BYTES_PER_PT_STEP * r["value"] / world / 1e9 / peak, "traffic": None,
-                     "kernel": "whole step per rank (K-ROW + K-COL + exchange)", "peak_source": peak_src},
+                     "kernel": "whole step per rank (K-ROW + K-COL + exchange)", "peak_source": peak_src,
+                     "kernels": r["kernels"]},
         "nvlink": {"bytes_per_gpu_per_step": r["a2a"]["nvlink_bytes_per_gpu_per_step"],
+                   "comm_stream_bytes_per_gpu_per_step": r["a2a"]["comm_stream_bytes_per_gpu_per_step"],
                    "a2a_ms_per_step_on_comm_stream": r["a2a"]["ms_per_step_on_comm_stream"],
-                   "achieved_gbs_per_direction": r["a2a"]["achieved_gbs_per_direction"], "peak_gbs": 770.0,
-                   "peak_source": "B200_PROFILING.md measured peer copy"},
+                   "comm_stream_gbs_per_direction": r["a2a"]["comm_stream_gbs_per_direction"],
+                   "whole_step_gbs_per_direction": r["a2a"]["whole_step_gbs_per_direction"],
+                   "peak_gbs": 770.0, "peak_source": "B200_PROFILING.md measured peer copy",
+                   "frac_of_peak_whole_step": (r["a2a"]["whole_step_gbs_per_direction"] or 0.0) / 770.0},
+        "t1": r.get("t1"), "parallel_efficiency": r.get("parallel_efficiency"),
+        "ensemble": r.get("ensemble"),
     }
     print(json.dumps(line))
 
@@ -451,22 +495,29 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="xfb", choices=["xfb", "reference"])
-    ap.add_argument("--grid", type=int, default=None, help="default 8192 (16384 with --slab)")
+    ap.add_argument("--grid", type=int, default=None, help="default 8192 at N = 1, 16384 (slab-decomposed) at N > 1")
     ap.add_argument("--members", type=int, default=1, help="ensemble members per GPU")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--e2e-inflight", type=int, default=3, help="independent requests in flight in the end-to-end measurement")
-    ap.add_argument("--ref-grid", type=int, default=2048, help="grid of the bounded CPU sample")
+    ap.add_argument("--ref-grid", type=int, default=0, help="grid of the CPU arm (default: the product arm's grid; the "
+                                                            "cpu_baseline leg inside the N = 1 product run uses --cpu-grid)")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds the timed run may take")
+    ap.add_argument("--cpu-grid", type=int, default=4096, help="grid of the bounded cpu_baseline sample inside the product run")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--slab", action="store_true", help="one grid slab-decomposed over the ranks (default: one ensemble member per GPU)")
-    ap.add_argument("--chunks", type=int, default=8, help="--slab: chunks of the compute/exchange overlap")
-    ap.add_argument("--slab-check", type=int, default=0, help="--slab: first verify against the single-GPU path at this grid size")
+    ap.add_argument("--slab", action="store_true", help="force the slab-decomposed arm (the default for N > 1)")
+    ap.add_argument("--ensemble", action="store_true", help="N > 1: independent members, one per GPU, as the headline")
+    ap.add_argument("--chunks", type=int, default=8, help="slab arm: chunks of the compute/exchange overlap")
+    ap.add_argument("--no-slab-check", action="store_true", help="slab arm: skip the in-run check against the single-GPU path and T1")
+    ap.add_argument("--no-ensemble-record", action="store_true", help="slab arm: skip the ensemble sub-record")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    slab = args.slab or ((world > 1 or args.gpus > 1) and not args.ensemble)
     if args.grid is None:
-        args.grid = 16384 if args.slab else 8192
+        args.grid = 16384 if slab else 8192
     if args.impl == "reference":
         reference_arm(args)
-    elif args.slab:
+    elif slab:
         slab_arm(args)
     else:
         gpu_arm(args)

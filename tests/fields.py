@@ -6,10 +6,12 @@ import numpy as np
 L = np.float32(600000.0)
 
 
-def _grid(n):
+def _grid(n, rows=None):
+    """rows = (r0, r1): only the grid rows i in [r0, r1) (a slab-decomposed rank generates its own rows)"""
     dx = np.float32(L / np.float32(n))
     x = (np.arange(n, dtype=np.float32) * dx).astype(np.float32)
-    return x[:, None], x[None, :]   # x = i*dx (slow), y = j*dy (fast)
+    xs = x if rows is None else x[rows[0]:rows[1]]
+    return xs[:, None], x[None, :]   # x = i*dx (slow), y = j*dy (fast)
 
 
 def _radius(x, y, cx, cy):
@@ -28,17 +30,39 @@ def gaussian(n):
     return (np.float64(np.float32(1e-3)) * np.exp(-(q * q))).astype(np.float32)
 
 
-def const_vortex(n):
-    """makefield-const-vortex.cpp:14-35"""
+def _lcg(seed, k):
+    """k-th output in [0, 1) of the 32-bit LCG x <- 1664525 x + 1013904223 started from `seed` (Numerical Recipes)"""
+    x = seed & 0xFFFFFFFF
+    for _ in range(k + 1):
+        x = (1664525 * x + 1013904223) & 0xFFFFFFFF
+    return x / 4294967296.0
+
+
+def gaussian_member(n, member):
+    """Member `member` of BASELINE.json's ensemble config (64 Gaussian vortices at 512^2).  The reference has no
+    ensemble and no RNG anywhere; members are the makefield-gaussian vortex with its centre moved by up to +-5 % of L
+    in x and y and its amplitude scaled by 1 +- 10 %, drawn from an LCG seeded with the member index.
+    Member 0 of a one-member ensemble is NOT special: use gaussian() for the reference generator's field."""
     x, y = _grid(n)
+    cx = np.float32(L * np.float32(0.5 + 0.1 * (_lcg(member, 0) - 0.5)))
+    cy = np.float32(L * np.float32(0.5 + 0.1 * (_lcg(member, 1) - 0.5)))
+    amp = np.float32(1e-3 * (1.0 + 0.2 * (_lcg(member, 2) - 0.5)))
+    r = _radius(x, y, cx, cy)
+    q = r.astype(np.float64) / 60000.0
+    return (np.float64(amp) * np.exp(-(q * q))).astype(np.float32)
+
+
+def const_vortex(n, rows=None):
+    """makefield-const-vortex.cpp:14-35"""
+    x, y = _grid(n, rows)
     c = np.float32(L / 2.0)
     r = _radius(x, y, c, c)
     return np.where(r <= np.float32(6000.0), np.float32(2e-5), np.float32(0)).astype(np.float32)
 
 
-def elliptic(n):
+def elliptic(n, rows=None):
     """makefield-elliptic-vortex.cpp:14-50"""
-    x, y = _grid(n)
+    x, y = _grid(n, rows)
     c = np.float32(L / 2.0)
     eps, lam, zeta0 = np.float32(0.7), np.float32(2.0), np.float32(0.005)
     r_i, r_o = np.float32(30000.0), np.float32(60000.0)

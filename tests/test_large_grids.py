@@ -1,15 +1,15 @@
-"""GPU checks at BASELINE.json's full sizes (4096^2, 8192^2), where the CPU oracle is too slow to run in a test:
-size-independent properties of the reference algorithm, and agreement of the kernel generations with one another.
+"""GPU checks at BASELINE.json's full sizes (4096^2, 8192^2) that complement the oracle comparisons of
+tests/test_headline_parity.py: size-independent properties of the reference algorithm, and agreement of the kernel
+generations with one another.
 
   * KAT-3 linear decay: a single mode has zero Jacobian, so one RK4 step multiplies a mode
     inside the dealiasing circle by 1 + z + z^2/2 + z^3/6 + z^4/24, z = -nu |k|^2 dt, and leaves a mode outside
     the circle untouched (the mask is applied to the tendency only, main.cpp:296-312).
   * KAT-5 invariants: mode (0,0) is constant, enstrophy does not grow.
   * the second-generation kernels (rowpair / colt, TMA-staged, persistent) must reproduce the first-generation
-    ones (XFB_ROW_SINGLE=1 XFB_COL_GEN1=1), the TMEM-park variant of K-ROW (XFB_ROW_TMEM=1) and the cluster variant of
-    K-COL (XFB_COL_CLUSTER=1) to float32 rounding: the
-    knobs are read once per process, so each variant runs in its own interpreter.
-  * one step at 2048^2 against the CPU oracle (the largest size the oracle finishes in a few seconds).
+    ones (XFB_ROW_SINGLE=1 XFB_COL_GEN1=1, the kernels 16384-point lines run on) and both park variants of K-ROW
+    (XFB_ROW_TMEM=0/1) to float32 rounding: the knobs are read once per process, so each variant runs in its own
+    interpreter.
 """
 import os
 import subprocess
@@ -125,8 +125,6 @@ def test_kernel_generations_agree(n, dt, tmp_path):
     assert np.isfinite(ref.view(np.float32)).all()
     # K-ROW with tensor-memory parks is the default at 8192 only: force it on and off everywhere
     variants = [{"XFB_ROW_SINGLE": "1", "XFB_COL_GEN1": "1"}, {"XFB_ROW_TMEM": "1"}, {"XFB_ROW_TMEM": "0"}]
-    if n == 8192:
-        variants.append({"XFB_COL_CLUSTER": "1"})
     for env in variants:
         got = _run_variant(n, dt, env, str(tmp_path / "variant.npy"))
         assert rel_l2(got, ref) < 2e-6, (env, rel_l2(got, ref))

@@ -163,6 +163,9 @@ extern "C" int xfb_slab_partition(int nx, int ny, int nranks, int nchunks, int r
     return 0;
 }
 
+static int create_body(xfb_handle h, int size_class, int nx, int ny, float lx, float ly, float nu, int batch, int device, int rank,
+                       int nranks, int nchunks);
+
 int xfb::create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float nu, int batch, int device, int rank, int nranks,
                      int nchunks)
 {
@@ -186,6 +189,18 @@ int xfb::create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float 
     xfb_handle h = new (std::nothrow) xfb_handle_s();
     if (!h) return fail(XFB_E_ARG, "xfb_create: out of host memory");
     memset(h, 0, sizeof(*h));
+    // every failure below releases what has been allocated so far (streams, events, device memory, the handle itself)
+    if (int e2 = create_body(h, size_class, nx, ny, lx, ly, nu, batch, device, rank, nranks, nchunks)) {
+        destroy_impl(h);
+        return e2;
+    }
+    *out = h;
+    return 0;
+}
+
+static int create_body(xfb_handle h, int size_class, int nx, int ny, float lx, float ly, float nu, int batch, int device, int rank,
+                       int nranks, int nchunks)
+{
     h->nx = nx; h->ny = ny; h->hy = ny / 2 + 1; h->batch = batch; h->device = device;
     h->lx = lx; h->ly = ly; h->nu = nu;
     h->tw_state = col_tile_width(nx);
@@ -200,7 +215,12 @@ int xfb::create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float 
             if ((unsigned)(((unsigned long long)k * h->cw_magic) >> 32) != k / (unsigned)h->pitch)
                 return fail(XFB_E_SIZE, "internal: magic division fails for k=%u cw=%d", k, h->pitch);
     }
-    if (size_class == 2) h->pitch = h->pitch_g = h->hy;       // generic path: reference layout, no padding
+    if (size_class == 2) {
+        // generic path: reference layout everywhere -- no padding, and the state arrays are ROW-major (tw_state = 0):
+        // a mixed grid such as 1024 x 768 has a fused-size nx but must not use the fused kernels' tile-major indexing
+        h->pitch = h->pitch_g = h->hy;
+        h->tw_state = 0;
+    }
     // `pitch` is the pitch of the column-side arrays (one chunk of this rank's columns; all columns on one GPU)
     h->grids = (size_t)h->rows * ny; h->hgrids = (size_t)nx * h->hy; h->hpad = (size_t)nx * h->pitch * nchunks;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -282,7 +302,6 @@ int xfb::create_impl(xfb_handle *out, int nx, int ny, float lx, float ly, float 
     }
     if (size_class == 2 && generic_create(h)) return XFB_E_CUDA;
     CK(cudaStreamSynchronize(h->stream));
-    *out = h;
     return 0;
 }
 
@@ -328,7 +347,8 @@ int xfb::destroy_impl(xfb_handle h)
         cudaEventDestroy(h->ev_fork);
         cudaStreamDestroy(h->comm_stream);
     }
-    cudaStreamDestroy(h->stream);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();          // a partially created handle (create failure) may have left harmless errors behind
     delete h;
     return 0;
 }
@@ -898,23 +918,29 @@ extern "C" int xfb_get_field_async(xfb_handle h, int member, int which, float *p
             CK(cudaEventCreateWithFlags(&h->rec_done[i], cudaEventDisableTiming));
         }
     }
-    const int slot = h->rec_next % XFB_NREC;
-    if (h->rec_next >= XFB_NREC) CK(cudaEventSynchronize(h->rec_done[slot]));        // the slot's previous copy has left
+    // rec_next is read by xfb_wait_field from another host thread (main.out's writer): atomic accesses, and the slot's
+    // events are recorded BEFORE the ticket is published
+    const int next = __atomic_load_n(&h->rec_next, __ATOMIC_RELAXED);
+    const int slot = next % XFB_NREC;
+    if (next >= XFB_NREC) CK(cudaEventSynchronize(h->rec_done[slot]));        // the slot's previous copy has left
     if (!h->rec_buf[slot] && dev_alloc((void **)&h->rec_buf[slot], sizeof(float) * h->grids)) return XFB_E_CUDA;
     if (field_to_device(h, member, which, h->rec_buf[slot])) return XFB_E_CUDA;
     CK(cudaEventRecord(h->rec_ready[slot], h->stream));
     CK(cudaStreamWaitEvent(h->rec_stream, h->rec_ready[slot], 0));
     CK(cudaMemcpyAsync(pinned_out, h->rec_buf[slot], sizeof(float) * h->grids, cudaMemcpyDeviceToHost, h->rec_stream));
     CK(cudaEventRecord(h->rec_done[slot], h->rec_stream));
-    *ticket = h->rec_next++;
+    *ticket = next;
+    __atomic_store_n(&h->rec_next, next + 1, __ATOMIC_RELEASE);
     return 0;
 }
 
 extern "C" int xfb_wait_field(xfb_handle h, int ticket)
 {
     if (!h) return fail(XFB_E_ARG, "null handle");
-    if (ticket < 0 || ticket >= h->rec_next) return fail(XFB_E_ARG, "bad ticket %d", ticket);
-    if (h->rec_next - ticket > XFB_NREC) return 0;              // its slot has been reused: that copy completed long ago
+    // thread-safe against a concurrent xfb_get_field_async on the same handle (one producer, one waiter)
+    const int next = __atomic_load_n(&h->rec_next, __ATOMIC_ACQUIRE);
+    if (ticket < 0 || ticket >= next) return fail(XFB_E_ARG, "bad ticket %d", ticket);
+    if (next - ticket > XFB_NREC) return 0;                     // its slot has been reused: that copy completed long ago
     CK(cudaSetDevice(h->device));
     CK(cudaEventSynchronize(h->rec_done[ticket % XFB_NREC]));
     return 0;

@@ -1,7 +1,6 @@
 // xfb_col.cu -- instantiations and launcher of the K-COL kernels.
 #include "xfb_internal.h"
 #include "xfb_colt.cuh"
-#include "xfb_coltc.cuh"
 
 namespace xfb {
 
@@ -63,16 +62,10 @@ template <int NX, int MODE>
 static int launch_colt_t(const ColParams &p, int batch, cudaStream_t st)
 {
     typedef ColTCfg<NX> C;
-    static int resident = 0;
-    if (resident == 0) {
-        cudaError_t e = cudaFuncSetAttribute(colt_kernel<NX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return (int)e;
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, colt_kernel<NX, MODE>, C::THREADS, C::SMEM);
-        resident = sms * (per_sm > 0 ? per_sm : 1);
-    }
+    static PerDeviceInt cfg;
+    int err = 0;
+    const int resident = cfg.get([&](int *e) { return resident_ctas(colt_kernel<NX, MODE>, C::THREADS, C::SMEM, 0, e); }, &err);
+    if (resident <= 0) return err;
     ColTMaps maps;
     const long long rows = (long long)NX * batch;
     if (MODE == COL_STEP || MODE == COL_FWDT || MODE == COL_TSTEP) {
@@ -94,45 +87,9 @@ static int launch_colt_t(const ColParams &p, int batch, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
-// NX = 8192: two-CTA clusters share a two-column tile (xfb_coltc.cuh)
-template <int NX, int MODE>
-static int launch_coltc_t(const ColParams &p, int batch, cudaStream_t st)
-{
-    typedef ColTCCfg<NX> C;
-    static int blocks_max = 0;
-    if (blocks_max == 0) {
-        cudaError_t e = cudaFuncSetAttribute(coltc_kernel<NX, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return (int)e;
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        blocks_max = sms & ~1;
-    }
-    ColTMaps maps;
-    const long long rows = (long long)NX * batch;
-    if (MODE == COL_STEP) {
-        if (int e = make_pair_map(&maps.jint, p.jint, rows, p.pitch, 2, C::BOXR)) return e;
-    } else {
-        maps.jint = CUtensorMap();
-    }
-    for (int f = 0; f < 4; ++f)
-        if (int e = make_pair_map(&maps.t[f], p.t_out[f], rows, p.pitch, 2, C::BOXR)) return e;
-    const int tiles_per_member = p.pitch / 2, tiles_total = tiles_per_member * batch;
-    const int blocks = 2 * tiles_total < blocks_max ? 2 * tiles_total : blocks_max;
-    coltc_kernel<NX, MODE><<<blocks, C::THREADS, C::SMEM, st>>>(p, maps, tiles_per_member, tiles_total);
-    return (int)cudaGetLastError();
-}
-
 template <int NX>
 static int launch_colt_n(int mode, const ColParams &p, int batch, cudaStream_t st)
 {
-    if constexpr (NX == 8192) {
-        // opt-in: measured SLOWER than colt_kernel<8192> (1.14 vs 0.92 ms per launch at 8192^2): the DSMEM
-        // redistribution and ten cluster barriers per tile cost more than the re-reads and the late fetch they remove
-        static const bool cluster = env_int("XFB_COL_CLUSTER", 0) != 0;
-        if (cluster && (mode == COL_STEP || mode == COL_PRO))
-            return mode == COL_STEP ? launch_coltc_t<NX, COL_STEP>(p, batch, st) : launch_coltc_t<NX, COL_PRO>(p, batch, st);
-    }
     if (mode == COL_DIAG) return launch_colt_t<NX, COL_DIAG>(p, batch, st);
     if (mode == COL_FWDT) return launch_colt_t<NX, COL_FWDT>(p, batch, st);
     if (mode == COL_TSTEP) return launch_colt_t<NX, COL_TSTEP>(p, batch, st);
@@ -144,12 +101,9 @@ template <int NX, int W, int MODE>
 static int launch_col_t(const ColParams &p, int batch, cudaStream_t st)
 {
     typedef ColCfg<NX, W> C;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(col_kernel<NX, W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static PerDeviceInt cfg;
+    int err = 0;
+    if (cfg.get([&](int *e) { return resident_ctas(col_kernel<NX, W, MODE>, C::THREADS, C::SMEM, 0, e); }, &err) <= 0) return err;
     dim3 grid(p.pitch / W, batch);
     col_kernel<NX, W, MODE><<<grid, C::THREADS, C::SMEM, st>>>(p);
     return (int)cudaGetLastError();

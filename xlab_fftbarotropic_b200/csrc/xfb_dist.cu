@@ -321,6 +321,23 @@ static int phase_barrier(Team *T, cudaStream_t st)
     return 0;
 }
 
+// Barrier over the ranks' COMPUTE streams: every rank has finished the work it has enqueued so far before any rank's
+// later work starts.  Needed wherever a receive array (tr[], jint_recv) is read by a kernel that is NOT followed by an
+// exchange phase of its own: a faster peer's next operation would otherwise push into the array while this rank is
+// still reading it (the trailing ROW_C2R of team_inverse, the COL_FWD of team_set_vorticity).  Inside the RK loop the
+// alternating phase barriers already give this ordering.
+static int team_fence(Team *T)
+{
+    xfb_handle h0 = T->local[0];
+    if (T->loopback || !h0->p2p) return 0;          // one stream / ncclRecv is posted by the receiver itself
+    CK(cudaEventRecord(h0->ev_chunk[0], h0->stream));
+    CK(cudaStreamWaitEvent(h0->comm_stream, h0->ev_chunk[0], 0));
+    if (int e = phase_barrier(T, h0->comm_stream)) return e;
+    CK(cudaEventRecord(h0->ev_comm[0], h0->comm_stream));
+    CK(cudaStreamWaitEvent(h0->stream, h0->ev_comm[0], 0));
+    return 0;
+}
+
 // events around the exchanges when profiling (NCCL transport only; the loopback shares the compute stream)
 static void a2a_mark(xfb_handle h, cudaStream_t st)
 {
@@ -418,7 +435,7 @@ static int team_set_vorticity(Team *T, const float *const *vort)
         h->have_state = true;
         h->tf_valid = false;
     }
-    return 0;
+    return team_fence(T);       // jint_recv has been consumed everywhere before anybody's next K-ROW stores into it
 }
 
 static int team_products(Team *T, int mode, int stage, float dt)
@@ -487,7 +504,7 @@ static int team_inverse(Team *T, const int *ops, int nops, int negate, float *co
         if (int e2 = launch_row_chunk(h, ROW_C2R, in, nullptr, nullptr, dout[l], negate, 0, h->rows)) return e2;
         h->tf_valid = false;                      // tr[0] was scratch
     }
-    return 0;
+    return team_fence(T);       // tr[0] has been consumed everywhere before anybody's next exchange pushes into it
 }
 
 static int team_get_field(Team *T, int which, float *const *dout)
@@ -654,7 +671,11 @@ extern "C" int xfb_create_dist(xfb_handle *out, int nx, int ny, float lx, float 
         cudaMemsetAsync(h->sync_buf, 0, sizeof(float), h->comm_stream);
         cudaStreamSynchronize(h->comm_stream);
         if (h->p2p)
-            if (int e = build_panel_table(h, h->peer_recv)) return e;
+            if (int e = build_panel_table(h, h->peer_recv)) {
+                dist_release(h);
+                *out = nullptr;
+                return e;
+            }
     }
     return 0;
 }
@@ -703,26 +724,39 @@ extern "C" int xfb_loopback_create(xfb_loopback_s **out, int nx, int ny, float l
     memset(L, 0, sizeof(*L));
     L->nx = nx; L->ny = ny;
     L->team.nranks = nranks; L->team.nlocal = nranks; L->team.loopback = true;
+    // a failure releases the ranks created so far
+    auto bail = [&](int e) {
+        for (int r = nranks - 1; r >= 0; --r) {
+            xfb_handle h = L->team.local[r];
+            if (!h) continue;
+            h->team = nullptr;
+            if (r > 0 && h->stream == L->team.local[0]->stream) h->stream = nullptr;     // shared with rank 0
+            destroy_impl(h);
+        }
+        if (L->full) cudaFree(L->full);
+        delete L;
+        return e;
+    };
     for (int r = 0; r < nranks; ++r) {
         xfb_handle h;
-        if (int e = create_impl(&h, nx, ny, lx, ly, nu, 1, device, r, nranks, nchunks)) return e;
+        if (int e = create_impl(&h, nx, ny, lx, ly, nu, 1, device, r, nranks, nchunks)) return bail(e);
+        L->team.local[r] = h;
         if (h->rows % nchunks != 0 || (h->rows / nchunks) % 2 != 0)
-            return fail(XFB_E_SIZE, "xfb_loopback_create: %d local rows do not split into %d even chunks", h->rows, nchunks);
+            return bail(fail(XFB_E_SIZE, "xfb_loopback_create: %d local rows do not split into %d even chunks", h->rows, nchunks));
         // every rank works on rank 0's stream: program order is the only synchronisation needed
         if (r > 0) {
             cudaStreamDestroy(h->stream);
             h->stream = L->team.local[0]->stream;
         }
         h->team = &L->team;
-        L->team.local[r] = h;
     }
     {
         cpx *recv[16];
         for (int r = 0; r < nranks; ++r) recv[r] = L->team.local[r]->recv_block;
         for (int r = 0; r < nranks; ++r)
-            if (int e = build_panel_table(L->team.local[r], recv)) return e;
+            if (int e = build_panel_table(L->team.local[r], recv)) return bail(e);
     }
-    if (dev_alloc((void **)&L->full, sizeof(float) * (size_t)nx * ny)) return XFB_E_CUDA;
+    if (dev_alloc((void **)&L->full, sizeof(float) * (size_t)nx * ny)) return bail(XFB_E_CUDA);
     *out = L;
     return 0;
 }

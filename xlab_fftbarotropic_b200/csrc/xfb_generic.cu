@@ -111,7 +111,10 @@ __global__ void gen_rows_r2c(const GenParams g, const float *__restrict__ in, cp
 }
 
 // rows: half spectrum -> real line, unnormalised * scale; Im of the DC and Nyquist bins ignored like FFTW's c2r
-__global__ void gen_rows_c2r(const GenParams g, const cpx *__restrict__ in, float *__restrict__ out, const float scale)
+// div != 0: the result is DIVIDED by div = (float)GRIDS like fftwf_backward_normalize (main.cpp:37-41) -- a multiplication
+// by 1/GRIDS differs by 1 ulp on grids that are not powers of two (768^2) --, then multiplied by scale (+-1)
+__global__ void gen_rows_c2r(const GenParams g, const cpx *__restrict__ in, float *__restrict__ out, const float scale,
+                             const float div)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     cpx *a = reinterpret_cast<cpx *>(smem), *b = a + g.ny;
@@ -124,7 +127,10 @@ __global__ void gen_rows_c2r(const GenParams g, const cpx *__restrict__ in, floa
     }
     __syncthreads();
     const cpx *r = gen_fft<-1>(a, b, g.ny, 1, g.facy, g.nfy, g.twy, blockDim.x);
-    for (int j = threadIdx.x; j < g.ny; j += blockDim.x) out[row * g.ny + j] = r[j].x * scale;
+    for (int j = threadIdx.x; j < g.ny; j += blockDim.x) {
+        const float x = (div != 0.0f) ? __fdiv_rn(r[j].x, div) : r[j].x;
+        out[row * g.ny + j] = __fmul_rn(x, scale);
+    }
 }
 
 // columns: complex transform along x for a tile of w adjacent columns
@@ -283,7 +289,12 @@ int generic_inv2d(xfb_handle h, const cpx *spec_in, cpx *tmp, float *real_out, f
     GenericPlan *P = (GenericPlan *)h->generic;
     const int tiles = (h->hy + P->cols_w - 1) / P->cols_w;
     GLAUNCH(h, (gen_cols<-1><<<tiles, 256, P->smem_cols, h->stream>>>(P->g, spec_in, tmp, P->cols_w)));
-    GLAUNCH(h, (gen_rows_c2r<<<h->nx, P->row_threads, P->smem_rows, h->stream>>>(P->g, tmp, real_out, negate ? -scale : scale)));
+    // the reference normalisation is a division by (float)GRIDS: keep that expression when the caller asks for 1/GRIDS
+    const float grids = (float)((double)h->nx * (double)h->ny);
+    const bool norm = (scale == 1.0f / grids);
+    const float mul = norm ? 1.0f : scale;
+    GLAUNCH(h, (gen_rows_c2r<<<h->nx, P->row_threads, P->smem_rows, h->stream>>>(P->g, tmp, real_out, negate ? -mul : mul,
+                                                                                  norm ? grids : 0.0f)));
     return 0;
 }
 

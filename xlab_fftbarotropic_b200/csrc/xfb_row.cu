@@ -19,12 +19,9 @@ static int launch_row_t(const RowParams &p, cudaStream_t st)
 {
     typedef RowCfg<NY> C;
     constexpr int smem = (MODE == ROW_JAC) ? C::SMEM_JAC : C::SMEM;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(row_kernel<NY, MODE, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static PerDeviceInt cfg;
+    int err = 0;
+    if (cfg.get([&](int *e) { return resident_ctas(row_kernel<NY, MODE, DIST>, C::THREADS, smem, 0, e); }, &err) <= 0) return err;
     const int blocks = (p.nrows + C::LPC - 1) / C::LPC;
     row_kernel<NY, MODE, DIST><<<blocks, C::THREADS, smem, st>>>(p);
     return (int)cudaGetLastError();
@@ -36,26 +33,14 @@ static int launch_pair_t(const RowParams &p, cudaStream_t st)
 {
     typedef PairCfg<NY> C;
     constexpr int smem = (MODE == ROW_JAC || MODE == ROW_DIAG) ? C::SMEM_JAC : C::SMEM;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(rowpair_kernel<NY, MODE, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static PerDeviceInt cfg;
+    int err = 0;
+    const int resident = cfg.get([&](int *e) { return resident_ctas(rowpair_kernel<NY, MODE, DIST>, C::THREADS, smem, 0, e); }, &err);
+    if (resident <= 0) return err;
     const int npairs = p.nrows / 2;
     int blocks = (npairs + C::PPC - 1) / C::PPC;
-    if ((MODE == ROW_JAC || MODE == ROW_DIAG) && !DIST) {
-        // persistent: as many CTAs as are resident at once, each walks over pair groups
-        static int resident = 0;
-        if (resident == 0) {
-            int dev = 0, sms = 0, per_sm = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rowpair_kernel<NY, MODE, DIST>, C::THREADS, smem);
-            resident = sms * (per_sm > 0 ? per_sm : 1);
-        }
-        if (blocks > resident) blocks = resident;
-    }
+    // persistent: as many CTAs as are resident at once, each walks over pair groups
+    if ((MODE == ROW_JAC || MODE == ROW_DIAG) && !DIST && blocks > resident) blocks = resident;
     rowpair_kernel<NY, MODE, DIST><<<blocks, C::THREADS, smem, st>>>(p);
     return (int)cudaGetLastError();
 }
@@ -69,17 +54,10 @@ template <int NY>
 static int launch_pair_tmem(const RowParams &p, cudaStream_t st)
 {
     typedef PairTCfg<NY> C;
-    static int resident = 0;
-    if (resident == 0) {
-        cudaError_t e = cudaFuncSetAttribute(rowpair_jac_tmem_kernel<NY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return (int)e;
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rowpair_jac_tmem_kernel<NY>, C::THREADS, C::SMEM);
-        if (per_sm * C::TCOLS > 512) per_sm = 512 / C::TCOLS;            // TMEM columns are a per-SM resource too
-        resident = sms * (per_sm > 0 ? per_sm : 1);
-    }
+    static PerDeviceInt cfg;
+    int err = 0;
+    const int resident = cfg.get([&](int *e) { return resident_ctas(rowpair_jac_tmem_kernel<NY>, C::THREADS, C::SMEM, C::TCOLS, e); }, &err);
+    if (resident <= 0) return err;
     const int npairs = p.nrows / 2;
     int blocks = (npairs + C::PPC - 1) / C::PPC;
     if (blocks > resident) blocks = resident;
