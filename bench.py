@@ -511,6 +511,12 @@ def main():
     ap.add_argument("--no-slab-check", action="store_true", help="slab arm: skip the in-run check against the single-GPU path and T1")
     ap.add_argument("--no-ensemble-record", action="store_true", help="slab arm: skip the ensemble sub-record")
     args = ap.parse_args()
+    # ONE JSON line on stdout: libraries write there too (NCCL prints "NCCL version ..." when NCCL_DEBUG is set), so the
+    # process-level stdout goes to stderr while the bench runs and the JSON line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     slab = args.slab or ((world > 1 or args.gpus > 1) and not args.ensemble)
     if args.grid is None:

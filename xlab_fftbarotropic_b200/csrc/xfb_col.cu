@@ -97,21 +97,36 @@ static int launch_colt_n(int mode, const ColParams &p, int batch, cudaStream_t s
     return mode == COL_STEP ? launch_colt_t<NX, COL_STEP>(p, batch, st) : launch_colt_t<NX, COL_PRO>(p, batch, st);
 }
 
-template <int NX, int W, int MODE>
+template <int NX, int W, int MODE, bool PEER = false>
 static int launch_col_t(const ColParams &p, int batch, cudaStream_t st)
 {
     typedef ColCfg<NX, W> C;
     static PerDeviceInt cfg;
     int err = 0;
-    if (cfg.get([&](int *e) { return resident_ctas(col_kernel<NX, W, MODE>, C::THREADS, C::SMEM, 0, e); }, &err) <= 0) return err;
+    if (cfg.get([&](int *e) { return resident_ctas(col_kernel<NX, W, MODE, PEER>, C::THREADS, C::SMEM, 0, e); }, &err) <= 0) return err;
     dim3 grid(p.pitch / W, batch);
-    col_kernel<NX, W, MODE><<<grid, C::THREADS, C::SMEM, st>>>(p);
+    col_kernel<NX, W, MODE, PEER><<<grid, C::THREADS, C::SMEM, st>>>(p);
     return (int)cudaGetLastError();
 }
+
+// fused column -> row exchange (ColParams::peer_rows > 0): instantiated for the slab grid of BASELINE.json (16384) and for
+// the two small sizes tests/test_slab.py forces onto this kernel
+template <int NX>
+constexpr bool col_peer_size() { return NX == 16384 || NX == 512 || NX == 1024; }
 
 template <int NX, int W>
 static int launch_col_n(int mode, const ColParams &p, int batch, cudaStream_t st)
 {
+    if (p.peer_rows > 0) {
+        if constexpr (col_peer_size<NX>()) {
+            switch (mode) {
+            case COL_INV: return launch_col_t<NX, W, COL_INV, true>(p, batch, st);
+            case COL_STEP: return launch_col_t<NX, W, COL_STEP, true>(p, batch, st);
+            case COL_PRO: return launch_col_t<NX, W, COL_PRO, true>(p, batch, st);
+            }
+        }
+        return (int)cudaErrorNotSupported;
+    }
     switch (mode) {
     case COL_FWD: return launch_col_t<NX, W, COL_FWD>(p, batch, st);
     case COL_INV: return launch_col_t<NX, W, COL_INV>(p, batch, st);

@@ -51,6 +51,16 @@ struct ColParams {
     float dt_stage;       // dt/2, dt/2, dt for stages 1..3
     int stage;            // 1..4 ; COL_DIAG: product set (0 strain, 1 tracer, 2 + field id: one record field)
     int nfields;          // COL_DIAG: number of products (3 or 1)
+    // slab-decomposed runs, fused column -> row exchange (peer_rows > 0): the x-inverse-transformed products are not written
+    // to the local t_out arrays for a push kernel to move afterwards; every row is stored straight into the receive
+    // array of the rank that owns it (CUDA-IPC peer mapping over NVLink, or this rank's own).  Rank R owns the rows
+    // [R * peer_rows, (R + 1) * peer_rows); peer_out[R * 4 + f] points at the block of receive array f of rank R that
+    // holds THIS rank's column chunks, peer_chunk_off selects the chunk of this launch; inside the block the rows are in
+    // the pair layout with pitch `pitch` (= columns per chunk).
+    int peer_rows;        // 0: local output
+    int peer_rows_shift;  // log2(peer_rows)
+    long long peer_chunk_off;
+    cpx *peer_out[16 * 4];
 };
 
 template <int NX, int W>
@@ -70,6 +80,22 @@ __device__ __forceinline__ size_t pair_base(const int t, const int j, const int 
 {
     return ((size_t)(t >> 1) * (size_t)pitch + (size_t)j) * 2 + (size_t)(t & 1);
 }
+
+// address of output element (row i = t + k * G, tile column jc) of product f: local pair-layout array, or the owning
+// rank's receive array.  G divides peer_rows (checked on the host), so the owner of row t + k * G is that of row k * G:
+// uniform over the CTA, one parameter-space lookup.
+// PEER is a template parameter: the local path must compile to one base address + constant offsets (a run-time test of
+// p.peer_rows in the store loops cost the single-GPU 16384^2 step 20 %: 36.8 -> 44.9 ms).
+template <int NX, bool PEER>
+__device__ __forceinline__ cpx *col_out_addr(const ColParams &p, const int f, cpx *local_base, const int t, const int jc, const int k)
+{
+    constexpr int G = NX / 16;
+    if (!PEER) return local_base + pair_base(t, jc, p.pitch) + (size_t)(k * G) * p.pitch;
+    const int R = (k * G) >> p.peer_rows_shift;
+    const int rl = (t + k * G) & (p.peer_rows - 1);
+    return p.peer_out[R * 4 + f] + p.peer_chunk_off + (((size_t)(rl >> 1) * (size_t)p.pitch + (size_t)jc) * 2 + (size_t)(rl & 1));
+}
+
 
 // -(kx^2 + ky^2) narrowed to float, summed in float64 like pow(float,2)+pow(float,2) (fftwfop.cpp:42-45)
 __device__ __forceinline__ float lap_coe(const double kx2, const double ky2) { return (float)(-(kx2 + ky2)); }
@@ -131,7 +157,7 @@ __device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&
     col_fft<NX, W, NIT, ColFftNoHook>(v, sm, t, c, tw, drain_tma, nohook);
 }
 
-template <int NX, int W, int MODE>
+template <int NX, int W, int MODE, bool PEER = false>
 __global__ void __launch_bounds__(ColCfg<NX, W>::THREADS, ColCfg<NX, W>::MINB)
 col_kernel(const ColParams p)
 {
@@ -257,9 +283,8 @@ col_kernel(const ColParams p)
         col_fft<NX, W, NIT>(v, sm, t, c, tw);
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            cpx *dst = p.t_out[0] + moff + pair_base(t[it], j0 + c[it], p.pitch);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) dst[(size_t)(k * G) * p.pitch] = cswap(v[it][k]);
+            for (int k = 0; k < 16; ++k) *col_out_addr<NX, PEER>(p, 0, p.t_out[0] + moff, t[it], j0 + c[it], k) = cswap(v[it][k]);
         }
     }
 
@@ -306,9 +331,8 @@ col_kernel(const ColParams p)
             cpx *outp = p.t_out[f];
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
-                cpx *dst = outp + moff + pair_base(t[it], j0 + c[it], p.pitch);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) dst[(size_t)(k * G) * p.pitch] = cswap(v[it][k]);
+                for (int k = 0; k < 16; ++k) *col_out_addr<NX, PEER>(p, f, outp + moff, t[it], j0 + c[it], k) = cswap(v[it][k]);
             }
         }
     }

@@ -107,6 +107,19 @@ static int build_panel_table(xfb_handle h, cpx *const *recv_of_rank)
         for (int c = 0; c < h->nchunks; ++c) tab[q * h->nchunks + c] = recv_of_rank[q] + col_off(h, h->rank, c, 0);
     if (dev_alloc((void **)&h->panel_base, sizeof(cpx *) * n)) return XFB_E_CUDA;
     CK(cudaMemcpy(h->panel_base, tab.data(), sizeof(cpx *) * n, cudaMemcpyHostToDevice));
+    // Fused column -> row exchange, OPT-IN (XFB_SLAB_FUSED_COL=1): K-COL stores each product row straight into the
+    // receive array tr[f] of the rank that owns the row (array 1 + f of that rank's receive block), at the block of
+    // panels (me, 0 .. nchunks-1).  Served by the first-generation column kernel (the line lengths > 8192 run on it).
+    // Measured on 2 GPUs at 16384^2 it is SLOWER than writing locally and pushing contiguous blocks (41.2 vs 38.1 ms per
+    // step): a one-column tile stores 16-byte pieces, fine for the local L2 but small NVLink packets; the push moves
+    // 2 KB runs.  Kept as an A/B knob (tests/test_slab.py checks it bit for bit).
+    static const bool col_on_knob = getenv("XFB_SLAB_FUSED_COL") && atoi(getenv("XFB_SLAB_FUSED_COL")) != 0;
+    static const bool gen1 = getenv("XFB_COL_GEN1") && atoi(getenv("XFB_COL_GEN1")) != 0;
+    const int G = h->nx / 16;
+    h->fused_col = col_on_knob && (h->nx == 16384 || (gen1 && (h->nx == 512 || h->nx == 1024))) && h->rows % G == 0 &&
+                   (h->rows & (h->rows - 1)) == 0;
+    for (int q = 0; q < h->nranks; ++q)
+        for (int f = 0; f < 4; ++f) h->peer_tr[q][f] = recv_of_rank[q] + (size_t)(1 + f) * h->hpad + row_off(h, h->rank, 0, 0);
     return 0;
 }
 
@@ -305,6 +318,14 @@ static int launch_col_chunk(xfb_handle h, int mode, int chunk, int stage, float 
     if (mode == COL_INV) { c.inv_in = inv_in + off; c.t_out[0] = inv_out + off; }
     c.dt = dt; c.stage = stage;
     c.dt_stage = (stage == 3) ? dt : dt / 2.0f;          // main.cpp:296,299,302
+    if (h->fused_col && mode != COL_FWD) {
+        c.peer_rows = h->rows;
+        c.peer_rows_shift = 0;
+        while ((1 << c.peer_rows_shift) < h->rows) ++c.peer_rows_shift;
+        c.peer_chunk_off = (long long)chunk * h->rows * h->pitch;          // panels (me, chunk): rows * cw elements each
+        for (int q = 0; q < h->nranks; ++q)
+            for (int f = 0; f < 4; ++f) c.peer_out[q * 4 + f] = h->peer_tr[q][f];
+    }
     CKL(h, launch_col(h->nx, mode, c, 1, h->stream));
     return 0;
 }
@@ -395,6 +416,19 @@ static int cols_then_exchange(Team *T, F produce, GC col_of, GR row_of, int na)
     cpx *rp[16 * 4], *cp[16 * 4];
     for (int l = 0; l < T->nlocal; ++l)
         for (int a = 0; a < na; ++a) { rp[l * na + a] = row_of(T->local[l], a); cp[l * na + a] = col_of(T->local[l], a); }
+    if (h0->fused_col) {
+        // fused exchange: the kernels have stored into the owners' receive arrays themselves; what is left is the barrier
+        for (int l = 0; l < T->nlocal; ++l)
+            for (int c = 0; c < C; ++c)
+                if (int e = produce(T->local[l], c)) return e;
+        if (T->loopback) return 0;
+        CK(cudaEventRecord(h0->ev_chunk[0], h0->stream));
+        CK(cudaStreamWaitEvent(h0->comm_stream, h0->ev_chunk[0], 0));
+        if (int e = phase_barrier(T, h0->comm_stream)) return e;
+        CK(cudaEventRecord(h0->ev_comm[1], h0->comm_stream));
+        CK(cudaStreamWaitEvent(h0->stream, h0->ev_comm[1], 0));
+        return 0;
+    }
     if (T->loopback) {
         for (int l = 0; l < T->nlocal; ++l)
             for (int c = 0; c < C; ++c)
@@ -666,7 +700,11 @@ extern "C" int xfb_create_dist(xfb_handle *out, int nx, int ny, float lx, float 
         // stepper kernels (NX, NY <= 8192) leave no SM free for a concurrent push kernel, so those grids default to ce.
         const char *push = getenv("XFB_SLAB_PUSH");
         h->push_sm = push ? (strcmp(push, "sm") == 0) : (nx > 8192 || ny > 8192);
-        h->push_blocks = 2;     // measured on 8 GPUs at 16384^2: 1 -> 8.7, 2 -> 7.7, 4 -> 7.9 ms per step
+        // CTAs per segment of the push kernel: a column -> row exchange of one chunk has nranks * 4 segments; enough CTAs to
+        // keep NVLink busy without starving the transform kernels (8 GPUs at 16384^2: 1 -> 8.7, 2 -> 7.7, 4 -> 7.9 ms per
+        // step; on 2 GPUs 2 CTAs per segment = 16 CTAs in all only reached 187 GB/s and the exchange bounded the step: 34.3 ms)
+        // 2 GPUs: 8 -> 25.4, 16 -> 24.6, 32 -> 25.6 ms per step
+        h->push_blocks = nranks >= 8 ? 2 : 32 / nranks;
         if (const char *pb = getenv("XFB_SLAB_PUSH_BLOCKS")) h->push_blocks = atoi(pb) < 1 ? 1 : atoi(pb);
         cudaMemsetAsync(h->sync_buf, 0, sizeof(float), h->comm_stream);
         cudaStreamSynchronize(h->comm_stream);
@@ -686,7 +724,11 @@ extern "C" int xfb_slab_transport(xfb_handle h)
     return h->p2p ? (h->push_sm ? 3 : 2) : 1;   // 3: SM push kernel, 2: copy-engine pushes (both over CUDA IPC peer mappings), 1: ncclSend/ncclRecv
 }
 
-extern "C" int xfb_slab_fused(xfb_handle h) { return (h && h->nranks > 1 && h->panel_base) ? 1 : 0; }
+extern "C" int xfb_slab_fused(xfb_handle h)
+{
+    if (!h || h->nranks <= 1) return 0;
+    return (h->panel_base ? 1 : 0) | (h->fused_col ? 2 : 0);       // bit 0: row -> column in K-ROW, bit 1: column -> row in K-COL
+}
 
 extern "C" int xfb_profile_read_a2a(xfb_handle h, double *a2a_ms, long long *exchanges)
 {
