@@ -106,10 +106,13 @@ int xfb_host_free(float *p);
 int xfb_get_field_async(xfb_handle h, int member, int which, float *pinned_out, int *ticket);
 int xfb_wait_field(xfb_handle h, int ticket);
 /* filamentation time and deformation factor together, from one set of second derivatives of psi (the two
- * XFB_TFIL / XFB_DEFORM calls of xfb_get_field recompute them); either output may be NULL */
+ * XFB_TFIL / XFB_DEFORM calls of xfb_get_field recompute them); either output may be NULL.  Slab-decomposed handles:
+ * the LOCAL rows, collective. */
 int xfb_get_diagnostics(xfb_handle h, int member, float *tfil, float *deform);
 /* effective-diffusivity histograms (README.md:6, Hendricks & Schubert 2009): per bin of the
- * tracer zeta in [cmin,cmax): area and integral of |grad zeta|^2 (float64[nbins] each, host) */
+ * tracer zeta in [cmin,cmax): area and integral of |grad zeta|^2 (float64[nbins] each, host).  Slab-decomposed
+ * handles: every rank bins its rows, ONE ncclAllReduce sums the 2 * nbins values, every rank receives the whole-domain
+ * histograms; collective. */
 int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cmax, double *area, double *grad2);
 
 /* ---- passive tracer (the reference has none) -------------------------
@@ -159,6 +162,8 @@ int xfb_loopback_set_vorticity(xfb_loopback t, const float *vort);
 int xfb_loopback_set_source(xfb_loopback t, const float *src);
 int xfb_loopback_step(xfb_loopback t, int nsteps, float dt);
 int xfb_loopback_get_field(xfb_loopback t, int which, float *out);
+int xfb_loopback_get_diagnostics(xfb_loopback t, float *tfil, float *deform);
+int xfb_loopback_get_keff_hist(xfb_loopback t, int nbins, float cmin, float cmax, double *area, double *grad2);
 long long xfb_loopback_launch_count(xfb_loopback t);
 
 /* ---- introspection --------------------------------------------------------------------------*/

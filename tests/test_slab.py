@@ -217,3 +217,38 @@ def test_loopback_fused_column_to_row_exchange(n, p, c, tmp_path):
     for k in ("vort", "u", "psi"):
         assert np.isfinite(res["fused"][k]).all()
         assert np.array_equal(res["fused"][k], res["copies"][k]), k
+
+
+@pytest.mark.gpu
+def test_loopback_diagnostics_and_keff_histograms():
+    """slab handles: both strain diagnostics from one set of second derivatives, and the effective-diffusivity histograms
+    binned per rank and summed over the ranks (the ncclAllReduce of the multi-process path is the shared accumulator of
+    the loopback team), against the single-GPU results"""
+    import xlab_fftbarotropic_b200 as xfb
+    n, p, c = 512, 4, 2
+    v0 = fields.elliptic(n)
+    one = xfb.Backend(n)
+    team = xfb.LoopbackTeam(n, p, c)
+    one.set_vorticity(v0)
+    team.set_vorticity(v0)
+    one.step(2, 3.0)
+    team.step(2, 3.0)
+    t1, d1 = one.diagnostics()
+    t2, d2 = team.diagnostics()
+    assert rel_l2(d2, d1) < 1e-5
+    clear = np.abs(d1) > 1e-4
+    assert np.array_equal((t2 > 0)[clear], (t1 > 0)[clear])
+    well = (d1 >= 0.05) & (t1 > 0) & (t2 > 0)
+    assert well.mean() > 0.3 and rel_l2(t2[well], t1[well]) < 1e-5
+    lo, hi = float(v0.min()) - 1e-6, float(v0.max()) * 1.01
+    a1, g1 = one.keff_hist(64, lo, hi)
+    a2, g2 = team.keff_hist(64, lo, hi)
+    assert abs(a2.sum() - 600000.0 ** 2) < 1e-6 * 600000.0 ** 2
+    assert rel_l2(np.cumsum(a2), np.cumsum(a1)) < 1e-5
+    assert rel_l2(np.cumsum(g2), np.cumsum(g1)) < 1e-5
+    # the state is untouched by the diagnostics
+    one.step(1, 3.0)
+    team.step(1, 3.0)
+    assert rel_l2(team.get_field(xfb.capi.VORT), one.get_field(xfb.capi.VORT)) < 2e-6
+    one.close()
+    team.close()

@@ -25,7 +25,8 @@ SYMBOLS = [
     "xfb_invert_pres", "xfb_launch_count", "xfb_stream", "xfb_size_supported", "xfb_profile", "xfb_profile_read",
     "xfb_slab_partition", "xfb_nccl_unique_id", "xfb_create_dist", "xfb_profile_read_a2a", "xfb_slab_transport", "xfb_slab_fused",
     "xfb_loopback_create", "xfb_loopback_destroy", "xfb_loopback_set_vorticity", "xfb_loopback_set_source",
-    "xfb_loopback_step", "xfb_loopback_get_field", "xfb_loopback_launch_count",
+    "xfb_loopback_step", "xfb_loopback_get_field", "xfb_loopback_launch_count", "xfb_loopback_get_diagnostics",
+    "xfb_loopback_get_keff_hist",
 ]
 
 _lib = None
@@ -87,6 +88,8 @@ def load():
     L.xfb_loopback_set_source.argtypes = [vp, vp]
     L.xfb_loopback_step.argtypes = [vp, ci, cf]
     L.xfb_loopback_get_field.argtypes = [vp, ci, vp]
+    L.xfb_loopback_get_diagnostics.argtypes = [vp, vp, vp]
+    L.xfb_loopback_get_keff_hist.argtypes = [vp, ci, cf, cf, vp, vp]
     L.xfb_loopback_launch_count.restype = C.c_longlong
     L.xfb_loopback_launch_count.argtypes = [vp]
     _lib = L
@@ -299,6 +302,12 @@ class SlabBackend(Backend):
         self._ck(self._L.xfb_get_field(self._h, 0, which, _ptr(out)))
         return out
 
+    def diagnostics(self, member=0):
+        t = np.empty((self.rows, self.ny), np.float32)
+        d = np.empty((self.rows, self.ny), np.float32)
+        self._ck(self._L.xfb_get_diagnostics(self._h, 0, _ptr(t), _ptr(d)))
+        return t, d
+
     @property
     def transport(self):
         t = {0: "none", 1: "nccl send/recv", 2: "p2p copy engines (CUDA IPC)", 3: "p2p SM push kernel (CUDA IPC)"}[int(self._L.xfb_slab_transport(self._h))]
@@ -363,6 +372,18 @@ class LoopbackTeam:
         out = np.empty((self.n, self.n), np.float32)
         self._ck(self._L.xfb_loopback_get_field(self._t, which, _ptr(out)))
         return out
+
+    def diagnostics(self):
+        t = np.empty((self.n, self.n), np.float32)
+        d = np.empty((self.n, self.n), np.float32)
+        self._ck(self._L.xfb_loopback_get_diagnostics(self._t, _ptr(t), _ptr(d)))
+        return t, d
+
+    def keff_hist(self, nbins, cmin, cmax):
+        area = np.zeros(nbins, np.float64)
+        g2 = np.zeros(nbins, np.float64)
+        self._ck(self._L.xfb_loopback_get_keff_hist(self._t, nbins, cmin, cmax, _ptr(area), _ptr(g2)))
+        return area, g2
 
     @property
     def launch_count(self):

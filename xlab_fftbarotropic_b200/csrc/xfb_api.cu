@@ -994,8 +994,8 @@ extern "C" int xfb_get_diagnostics(xfb_handle h, int member, float *tfil, float 
     if (check_member(h, member)) return XFB_E_ARG;
     if (!tfil && !deform) return fail(XFB_E_ARG, "no output requested");
     if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_diagnostics before xfb_set_vorticity");
-    NO_SLAB(h, "xfb_get_diagnostics");
     CK(cudaSetDevice(h->device));
+    if (h->nranks > 1) return dist_diagnostics(h, tfil, deform);          // local rows; collective
     const size_t bytes = sizeof(float) * h->grids;
     const long long n = (long long)h->grids;
     if (fused_diag_ok(h)) {
@@ -1064,6 +1064,17 @@ __global__ void keff_hist_kernel(const float *c, const float *gx, const float *g
     }
 }
 
+int xfb::launch_keff_hist(xfb_handle h, const float *c, const float *gx, const float *gy, long long n, int nbins, float cmin,
+                          float cmax, double *d_area, double *d_grad2)
+{
+    const double da = ((double)h->lx / h->nx) * ((double)h->ly / h->ny);
+    const float scale = (float)nbins / (cmax - cmin);
+    keff_hist_kernel<<<296, 256, sizeof(double) * 2 * nbins, h->stream>>>(c, gx, gy, n, nbins, cmin, scale, da, d_area, d_grad2);
+    CK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
 static int keff_hist_impl(xfb_handle h, int member, int nbins, float cmin, float cmax, double *area, double *grad2,
                           const cpx *state)
 {
@@ -1079,12 +1090,8 @@ static int keff_hist_impl(xfb_handle h, int member, int nbins, float cmin, float
     }
     double *d = (double *)h->ref_a;
     CK(cudaMemsetAsync(d, 0, sizeof(double) * 2 * nbins, h->stream));
-    const double da = ((double)h->lx / h->nx) * ((double)h->ly / h->ny);
-    const float scale = (float)nbins / (cmax - cmin);
-    keff_hist_kernel<<<296, 256, sizeof(double) * 2 * nbins, h->stream>>>(h->real_a, h->real_b, fused ? nullptr : h->real_c, (long long)h->grids,
-                                                                           nbins, cmin, scale, da, d, d + nbins);
-    CK(cudaGetLastError());
-    h->launches++;
+    if (launch_keff_hist(h, h->real_a, h->real_b, fused ? nullptr : h->real_c, (long long)h->grids, nbins, cmin, cmax, d, d + nbins))
+        return XFB_E_CUDA;
     std::vector<double> host(2 * (size_t)nbins);
     CK(cudaMemcpyAsync(host.data(), d, sizeof(double) * 2 * nbins, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1097,7 +1104,12 @@ extern "C" int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin
 {
     if (check_member(h, member)) return XFB_E_ARG;
     if (!h->have_state) return fail(XFB_E_STATE, "xfb_get_keff_hist before xfb_set_vorticity");
-    NO_SLAB(h, "xfb_get_keff_hist");
+    if (h->nranks > 1) {
+        // slab handle: every rank bins its own rows, one all-reduce of the 2 * nbins sums; collective
+        if (!area || !grad2 || nbins < 1 || nbins > 2048 || !(cmax > cmin)) return fail(XFB_E_ARG, "bad histogram arguments");
+        CK(cudaSetDevice(h->device));
+        return dist_keff_hist(h, nbins, cmin, cmax, area, grad2);
+    }
     return keff_hist_impl(h, member, nbins, cmin, cmax, area, grad2, nullptr);
 }
 

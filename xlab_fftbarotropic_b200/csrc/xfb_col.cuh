@@ -111,16 +111,21 @@ __device__ __forceinline__ int signed_row(const int t, const int k)
     return i - NX;
 }
 
-// no-op hook of col_fft
+// no-op hooks of col_fft
 struct ColFftNoHook {
     __device__ __forceinline__ void operator()(int, bool) const {}
+};
+struct ColFftNoPre {
+    __device__ __forceinline__ void operator()() const {}
 };
 
 // hook(e, last): called by every thread after exchange e (0-based) has been read and its closing barrier passed --
 // a CTA-uniform point between two barriers where the caller can slip in unrelated pipelined work.
-template <int NX, int W, int NIT, class Hook>
+// pre(): called by every thread right before the shared-memory writes of the LAST exchange: global loads issued there
+// (the first operands of the caller's epilogue) complete under the exchange's two barriers and the final pass.
+template <int NX, int W, int NIT, class Hook, class Pre>
 __device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&t)[NIT], const int (&c)[NIT],
-                                        const LineTw<NX> (&tw)[NIT], const bool drain_tma, Hook &hook)
+                                        const LineTw<NX> (&tw)[NIT], const bool drain_tma, Hook &hook, Pre &pre)
 {
     typedef LinePlan<NX> P;
     // drain_tma (uniform over the CTA): the caller is going to overwrite a buffer that bulk stores may still be reading.
@@ -128,12 +133,14 @@ __device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&
     // drain under the earlier passes and every thread that leaves the transform knows the buffer is free.
     constexpr int LAST_EX = (P::NPASS > P::N16) ? P::N16 - 1 : P::N16 - 2;
     if (LAST_EX < 0 && drain_tma && threadIdx.x == 0) tma_wait_read_all();
+    if (LAST_EX < 0) pre();
     int ns = 1;
 #pragma unroll
     for (int p = 0; p < P::N16; ++p) {
 #pragma unroll
         for (int it = 0; it < NIT; ++it) pass16_compute<NX>(v[it], p, tw[it]);
         if (p != P::NPASS - 1) {
+            if (p == LAST_EX) pre();
 #pragma unroll
             for (int it = 0; it < NIT; ++it) exchange_write<W>(v[it], sm, t[it], c[it], ns);
             if (p == LAST_EX && drain_tma && threadIdx.x == 0) tma_wait_read_all();
@@ -147,6 +154,14 @@ __device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&
     }
 #pragma unroll
     for (int it = 0; it < NIT; ++it) rem_pass<NX>(v[it], tw[it]);
+}
+
+template <int NX, int W, int NIT, class Hook>
+__device__ __forceinline__ void col_fft(cpx (&v)[NIT][16], cpx *sm, const int (&t)[NIT], const int (&c)[NIT],
+                                        const LineTw<NX> (&tw)[NIT], const bool drain_tma, Hook &hook)
+{
+    ColFftNoPre nopre;
+    col_fft<NX, W, NIT, Hook, ColFftNoPre>(v, sm, t, c, tw, drain_tma, hook, nopre);
 }
 
 template <int NX, int W, int NIT>

@@ -238,66 +238,95 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
 #pragma unroll
                     for (int k = 0; k < 16; ++k) v[0][k] = src[k * G * TW];
                 }
-                col_fft<NX, FW, 1>(v, F, t, c, tw);
                 const int j = p.j_base + j0 + col;
                 const float kyv = __ldg(p.ky + j);
                 const float ky2 = kyv * kyv;
                 const size_t soff = moff + (size_t)(tl * NG + cg) * (size_t)p.st_tile_stride;
                 const size_t e0 = soff + (size_t)t[0] * srow + c[0];
+                // Epilogue operands (z0, zk, acc of this column group) in quarters of four rows.  The loads of the first
+                // quarter are issued INSIDE the forward transform, right before its last exchange, so that their L2
+                // latency passes under the exchange's two barriers and the final pass; the loads of quarter q + 1 are
+                // issued before the arithmetic of quarter q.  Measured NEUTRAL against one batch of 24 loads per half after
+                // the transform (8192^2: 0.785 vs 0.782 ms per launch, 4096^2: 0.153 both): the scoreboard samples of
+                // profiles/r01f_8192_stall_segments.txt seg 9 are where the warps wait, not what bounds the tile -- ten
+                // 8192-point transforms per tile (instruction issue + shared-memory exchange) do.
+                cpx qz0[4], qzk[4], qac[4];
+                auto pre = [&]() {
+                    if (MODE == COL_STEP) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) qz0[q] = p.z0[e0 + (size_t)(q * G) * srow];
+                        if (p.stage != 1) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                qzk[q] = p.zk[e0 + (size_t)(q * G) * srow];
+                                qac[q] = p.acc[e0 + (size_t)(q * G) * srow];
+                            }
+                        }
+                    }
+                };
+                ColFftNoHook nohook;
+                col_fft<NX, FW, 1, ColFftNoHook, decltype(pre)>(v, F, t, c, tw, false, nohook, pre);
                 if (MODE == COL_FWDT) {
                     // plain forward transform of the tile into the tile-major state (xfb_set_vorticity: main.cpp:256)
 #pragma unroll
                     for (int k = 0; k < 16; ++k) p.z0[e0 + (size_t)(k * G) * srow] = v[0][k];
                 }
+                cpx znew[TKEEP ? 8 : 1];
 #pragma unroll
-                for (int h = 0; h < (MODE == COL_FWDT ? 0 : 2); ++h) {
-                    cpx z0v[8], zkv[8], av[8];
+                for (int qd = 0; qd < (MODE == COL_FWDT ? 0 : 4); ++qd) {
+                    cpx nz0[4], nzk[4], nac[4];
+                    if (qd < 3) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) z0v[q] = p.z0[e0 + (size_t)((8 * h + q) * G) * srow];
-                    if (p.stage != 1) {
+                        for (int q = 0; q < 4; ++q) nz0[q] = p.z0[e0 + (size_t)((4 * qd + 4 + q) * G) * srow];
+                        if (p.stage != 1) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            zkv[q] = p.zk[e0 + (size_t)((8 * h + q) * G) * srow];
-                            av[q] = p.acc[e0 + (size_t)((8 * h + q) * G) * srow];
+                            for (int q = 0; q < 4; ++q) {
+                                nzk[q] = p.zk[e0 + (size_t)((4 * qd + 4 + q) * G) * srow];
+                                nac[q] = p.acc[e0 + (size_t)((4 * qd + 4 + q) * G) * srow];
+                            }
                         }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) { zkv[q] = z0v[q]; av[q] = mk(0.f, 0.f); }
                     }
-                    cpx znew[TKEEP ? 8 : 1];
+                    if (p.stage == 1) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int k = 8 * h + q;
+                        for (int q = 0; q < 4; ++q) { qzk[q] = qz0[q]; qac[q] = mk(0.f, 0.f); }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int k = 4 * qd + q;
                         const int i = t[0] + k * G;
                         const size_t e = e0 + (size_t)(k * G) * srow;
                         const cpx X = v[0][k];
                         const float kxv = (float)signed_row<NX>(t[0], k) * p.kxscale;
                         const float lap = -fmaf(kxv, kxv, ky2);
                         // dvortdt_c += (vort_c * laplacian_coe) * NU                                  main.cpp:240-243
-                        const float tx = __fadd_rn(X.x, __fmul_rn(__fmul_rn(zkv[q].x, lap), p.nu));
-                        const float ty2 = __fadd_rn(X.y, __fmul_rn(__fmul_rn(zkv[q].y, lap), p.nu));
+                        const float tx = __fadd_rn(X.x, __fmul_rn(__fmul_rn(qzk[q].x, lap), p.nu));
+                        const float ty2 = __fadd_rn(X.y, __fmul_rn(__fmul_rn(qzk[q].y, lap), p.nu));
                         // dealiasing mask (fftwfop.cpp:57-68)
                         const int ii = (i <= NX / 2) ? i : NX - i;
                         const float m = (ii * ii + j * j >= p.mask_kd_i) ? 0.0f : 1.0f;
                         const float rx = __fmul_rn(tx, m), ry = __fmul_rn(ty2, m);
                         cpx zn;
                         if (p.stage == 4) {                                                          // main.cpp:309-312
-                            zn.x = __fadd_rn(z0v[q].x, __fdiv_rn(__fmul_rn(__fadd_rn(av[q].x, rx), p.dt), 6.0f));
-                            zn.y = __fadd_rn(z0v[q].y, __fdiv_rn(__fmul_rn(__fadd_rn(av[q].y, ry), p.dt), 6.0f));
+                            zn.x = __fadd_rn(qz0[q].x, __fdiv_rn(__fmul_rn(__fadd_rn(qac[q].x, rx), p.dt), 6.0f));
+                            zn.y = __fadd_rn(qz0[q].y, __fdiv_rn(__fmul_rn(__fadd_rn(qac[q].y, ry), p.dt), 6.0f));
                             p.z0[e] = zn;
                         } else {                                                                     // main.cpp:246-251
                             const cpx an = (p.stage == 1) ? mk(rx, ry)
-                                                          : mk(__fadd_rn(av[q].x, __fmul_rn(2.0f, rx)),
-                                                               __fadd_rn(av[q].y, __fmul_rn(2.0f, ry)));
+                                                          : mk(__fadd_rn(qac[q].x, __fmul_rn(2.0f, rx)),
+                                                               __fadd_rn(qac[q].y, __fmul_rn(2.0f, ry)));
                             p.acc[e] = an;
-                            zn.x = __fadd_rn(z0v[q].x, __fmul_rn(rx, p.dt_stage));
-                            zn.y = __fadd_rn(z0v[q].y, __fmul_rn(ry, p.dt_stage));
+                            zn.x = __fadd_rn(qz0[q].x, __fmul_rn(rx, p.dt_stage));
+                            zn.y = __fadd_rn(qz0[q].y, __fmul_rn(ry, p.dt_stage));
                             p.zk[e] = zn;
                         }
                         if (KEEP) zkeep[k] = zn;
-                        if (TKEEP) znew[q] = zn;
+                        if (TKEEP) znew[(qd & 1) * 4 + q] = zn;
                     }
-                    if (TKEEP) tmem_park8(tpark + (unsigned)(cg * 32 + h * 16), reinterpret_cast<const cpx(&)[8]>(znew));
+                    if (TKEEP && (qd & 1)) tmem_park8(tpark + (unsigned)(cg * 32 + (qd >> 1) * 16), reinterpret_cast<const cpx(&)[8]>(znew));
+                    if (qd < 3) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { qz0[q] = nz0[q]; qzk[q] = nzk[q]; qac[q] = nac[q]; }
+                    }
                 }
             }
         }

@@ -573,7 +573,81 @@ static int team_get_field(Team *T, int which, float *const *dout)
     return fail(XFB_E_ARG, "bad field id %d", which);
 }
 
+// both strain diagnostics from ONE set of the three second derivatives of psi; either output list may be null
+static int team_diagnostics(Team *T, float *const *tfil, float *const *deform)
+{
+    static const int op_pxy[] = {OP_INVLAP, OP_GRADX, OP_GRADY}, op_pxx[] = {OP_INVLAP, OP_GRADX, OP_GRADX},
+                     op_pyy[] = {OP_INVLAP, OP_GRADY, OP_GRADY};
+    float *a[16], *b[16], *c[16];
+    for (int l = 0; l < T->nlocal; ++l) { a[l] = T->local[l]->real_a; b[l] = T->local[l]->real_b; c[l] = T->local[l]->real_c; }
+    if (int e = team_inverse(T, op_pxy, 3, 0, b)) return e;
+    if (int e = team_inverse(T, op_pxx, 3, 0, c)) return e;
+    if (int e = team_inverse(T, op_pyy, 3, 0, a)) return e;
+    for (int l = 0; l < T->nlocal; ++l) {
+        xfb_handle h = T->local[l];
+        const long long n = (long long)h->grids;
+        for (int o = 0; o < 2; ++o) {
+            float *out = o == 0 ? (tfil ? tfil[l] : nullptr) : (deform ? deform[l] : nullptr);
+            if (!out) continue;
+            dist_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(b[l], c[l], a[l], out, n, o == 0 ? XFB_TFIL : XFB_DEFORM);
+            CK(cudaGetLastError());
+            h->launches++;
+        }
+    }
+    return 0;
+}
+
+// effective-diffusivity histograms: zeta, zeta_x, zeta_y of the local rows, binned per rank into `d[l]` (2 * nbins doubles,
+// device); the caller reduces over the ranks
+static int team_keff_hist(Team *T, int nbins, float cmin, float cmax, double *const *d)
+{
+    static const int op_vort[] = {OP_COPY}, op_zx[] = {OP_GRADX}, op_zy[] = {OP_GRADY};
+    float *a[16], *b[16], *c[16];
+    for (int l = 0; l < T->nlocal; ++l) { a[l] = T->local[l]->real_a; b[l] = T->local[l]->real_b; c[l] = T->local[l]->real_c; }
+    if (int e = team_inverse(T, op_vort, 1, 0, a)) return e;
+    if (int e = team_inverse(T, op_zx, 1, 0, b)) return e;
+    if (int e = team_inverse(T, op_zy, 1, 0, c)) return e;
+    // the inverses above use the spectral scratch arrays the caller may have taken `d` from: zero it only now
+    CK(cudaMemsetAsync(d[0], 0, sizeof(double) * 2 * nbins, T->local[0]->stream));
+    for (int l = 1; l < T->nlocal; ++l)
+        if (d[l] != d[0]) CK(cudaMemsetAsync(d[l], 0, sizeof(double) * 2 * nbins, T->local[l]->stream));
+    for (int l = 0; l < T->nlocal; ++l) {
+        xfb_handle h = T->local[l];
+        if (int e = launch_keff_hist(h, a[l], b[l], c[l], (long long)h->grids, nbins, cmin, cmax, d[l], d[l] + nbins)) return e;
+    }
+    return 0;
+}
+
 // ---- entry points used by xfb_api.cu for NCCL handles ----------------------------------------------------
+int dist_keff_hist(xfb_handle h, int nbins, float cmin, float cmax, double *area, double *grad2)
+{
+    if (h->team->loopback) return fail(XFB_E_STATE, "loopback ranks are driven through xfb_loopback_*");
+    double *d = (double *)h->spec_a;                 // free scratch of >= 2 * 2048 doubles once the inverses are done
+    if (int e = team_keff_hist(h->team, nbins, cmin, cmax, &d)) return e;
+    // one all-reduce of the 2 * nbins partial sums over the ranks
+    NCK(g_nccl.AllReduce(d, d, (size_t)2 * nbins, ncclDouble, ncclSum, h->team->comm, h->stream));
+    std::vector<double> host(2 * (size_t)nbins);
+    CK(cudaMemcpyAsync(host.data(), d, sizeof(double) * 2 * nbins, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(area, host.data(), sizeof(double) * nbins);
+    memcpy(grad2, host.data() + nbins, sizeof(double) * nbins);
+    return 0;
+}
+
+int dist_diagnostics(xfb_handle h, float *tfil_rows, float *deform_rows)
+{
+    if (h->team->loopback) return fail(XFB_E_STATE, "loopback ranks are driven through xfb_loopback_*");
+    const size_t bytes = sizeof(float) * h->grids;
+    float *scratch = (float *)h->spec_b;             // >= grids floats, free after the last team_inverse
+    float *dt = tfil_rows ? (is_device_ptr(tfil_rows) ? tfil_rows : scratch) : nullptr;
+    float *dd = deform_rows ? (is_device_ptr(deform_rows) ? deform_rows : (float *)h->jint) : nullptr;
+    if (int e = team_diagnostics(h->team, dt ? &dt : nullptr, dd ? &dd : nullptr)) return e;
+    if (dt && dt != tfil_rows) CK(cudaMemcpyAsync(tfil_rows, dt, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (dd && dd != deform_rows) CK(cudaMemcpyAsync(deform_rows, dd, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int dist_set_vorticity(xfb_handle h, const float *vort_rows)
 {
     if (h->team->loopback) return fail(XFB_E_STATE, "loopback ranks are driven through xfb_loopback_*");
@@ -860,6 +934,47 @@ extern "C" int xfb_loopback_get_field(xfb_loopback_s *L, int which, float *out_f
     if (int e = team_get_field(&L->team, which, rows)) return e;
     CK(cudaMemcpyAsync(out_full_host, L->full, sizeof(float) * (size_t)L->nx * L->ny, cudaMemcpyDeviceToHost, h0->stream));
     CK(cudaStreamSynchronize(h0->stream));
+    return 0;
+}
+
+extern "C" int xfb_loopback_get_diagnostics(xfb_loopback_s *L, float *tfil_full_host, float *deform_full_host)
+{
+    if (!L || (!tfil_full_host && !deform_full_host)) return fail(XFB_E_ARG, "null argument");
+    xfb_handle h0 = L->team.local[0];
+    if (!h0->have_state) return fail(XFB_E_STATE, "xfb_loopback_get_diagnostics before xfb_loopback_set_vorticity");
+    CK(cudaSetDevice(h0->device));
+    const size_t n = (size_t)L->nx * L->ny;
+    float *second = nullptr;
+    if (tfil_full_host && deform_full_host && dev_alloc((void **)&second, sizeof(float) * n)) return XFB_E_CUDA;
+    float *t_rows[16], *d_rows[16];
+    float *tbuf = tfil_full_host ? L->full : nullptr, *dbuf = deform_full_host ? (tfil_full_host ? second : L->full) : nullptr;
+    for (int r = 0; r < L->team.nranks; ++r) {
+        t_rows[r] = tbuf ? tbuf + (size_t)r * h0->rows * L->ny : nullptr;
+        d_rows[r] = dbuf ? dbuf + (size_t)r * h0->rows * L->ny : nullptr;
+    }
+    int e = team_diagnostics(&L->team, tbuf ? t_rows : nullptr, dbuf ? d_rows : nullptr);
+    if (!e && tbuf) e = cudaMemcpyAsync(tfil_full_host, tbuf, sizeof(float) * n, cudaMemcpyDeviceToHost, h0->stream) != cudaSuccess;
+    if (!e && dbuf) e = cudaMemcpyAsync(deform_full_host, dbuf, sizeof(float) * n, cudaMemcpyDeviceToHost, h0->stream) != cudaSuccess;
+    cudaStreamSynchronize(h0->stream);
+    if (second) cudaFree(second);
+    return e ? XFB_E_CUDA : 0;
+}
+
+extern "C" int xfb_loopback_get_keff_hist(xfb_loopback_s *L, int nbins, float cmin, float cmax, double *area, double *grad2)
+{
+    if (!L || !area || !grad2 || nbins < 1 || nbins > 2048 || !(cmax > cmin)) return fail(XFB_E_ARG, "bad histogram arguments");
+    xfb_handle h0 = L->team.local[0];
+    if (!h0->have_state) return fail(XFB_E_STATE, "xfb_loopback_get_keff_hist before xfb_loopback_set_vorticity");
+    CK(cudaSetDevice(h0->device));
+    // all ranks share the device and the stream: their kernels accumulate into ONE buffer (the all-reduce of the NCCL path)
+    double *d[16];
+    for (int r = 0; r < L->team.nranks; ++r) d[r] = (double *)L->full;
+    if (int e = team_keff_hist(&L->team, nbins, cmin, cmax, d)) return e;
+    std::vector<double> host(2 * (size_t)nbins);
+    CK(cudaMemcpyAsync(host.data(), d[0], sizeof(double) * 2 * nbins, cudaMemcpyDeviceToHost, h0->stream));
+    CK(cudaStreamSynchronize(h0->stream));
+    memcpy(area, host.data(), sizeof(double) * nbins);
+    memcpy(grad2, host.data() + nbins, sizeof(double) * nbins);
     return 0;
 }
 

@@ -125,7 +125,14 @@ int generic_fwd2d(xfb_handle h, const float *real_in, cpx *tmp, cpx *spec_out);
 int generic_inv2d(xfb_handle h, const cpx *spec_in, cpx *tmp, float *real_out, float scale, int negate);
 int generic_step(xfb_handle h, int nsteps, float dt);
 
+// histogram of area and |grad c|^2 over tracer bins of `n` points (xfb_api.cu); accumulates into d_area[nbins], d_grad2[nbins]
+// (device, float64, zeroed by the caller); gy == nullptr: gx holds |grad c|^2
+int launch_keff_hist(xfb_handle h, const float *c, const float *gx, const float *gy, long long n, int nbins, float cmin, float cmax,
+                     double *d_area, double *d_grad2);
+
 // slab paths (xfb_dist.cu)
+int dist_keff_hist(xfb_handle h, int nbins, float cmin, float cmax, double *area, double *grad2);
+int dist_diagnostics(xfb_handle h, float *tfil_rows, float *deform_rows);
 int dist_set_vorticity(xfb_handle h, const float *vort_rows);
 int dist_step(xfb_handle h, int nsteps, float dt);
 int dist_get_field(xfb_handle h, int which, float *out_rows);
