@@ -119,12 +119,17 @@ def _run_variant(n, dt, env, out):
     return np.load(out)
 
 
-@pytest.mark.parametrize("n,dt", [(1024, 3.0), (4096, 1.0), (8192, 0.5)])
+@pytest.mark.parametrize("n,dt", [(1024, 3.0), (4096, 1.0), (8192, 0.5), (16384, 0.25)])
 def test_kernel_generations_agree(n, dt, tmp_path):
     ref = _run_variant(n, dt, {}, str(tmp_path / "default.npy"))
     assert np.isfinite(ref.view(np.float32)).all()
     # K-ROW with tensor-memory parks is the default at 8192 only: force it on and off everywhere
     variants = [{"XFB_ROW_SINGLE": "1", "XFB_COL_GEN1": "1"}, {"XFB_ROW_TMEM": "1"}, {"XFB_ROW_TMEM": "0"}]
+    if n == 4096:
+        variants.append({"XFB_COL_2L": "1"})          # the two-level K-COL of the 16384 grid, forced onto 4096-point columns
+    if n == 16384:
+        # the two-level kernels of 16384-point lines (defaults) against the first-generation ones, one at a time and both
+        variants = [{"XFB_COL_GEN1": "1"}, {"XFB_ROW_2L": "0"}, {"XFB_COL_GEN1": "1", "XFB_ROW_2L": "0"}]
     for env in variants:
         got = _run_variant(n, dt, env, str(tmp_path / "variant.npy"))
         assert rel_l2(got, ref) < 2e-6, (env, rel_l2(got, ref))

@@ -21,7 +21,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 CUDA_SOURCES = ["xfb_row.cu", "xfb_col.cu", "xfb_api.cu", "xfb_dist.cu", "xfb_generic.cu"]
-HEADERS = ["xfb_fft.cuh", "xfb_row.cuh", "xfb_rowpair.cuh", "xfb_col.cuh", "xfb_colt.cuh", "xfb_internal.h", "xfb_handle.h", os.path.join(ROOT, "include", "xfb.h")]
+HEADERS = ["xfb_fft.cuh", "xfb_row.cuh", "xfb_rowpair.cuh", "xfb_rowpair2l.cuh", "xfb_col.cuh", "xfb_colt.cuh", "xfb_col2l.cuh", "xfb_internal.h", "xfb_handle.h", os.path.join(ROOT, "include", "xfb.h")]
 
 
 def _mtime(p):

@@ -1,6 +1,7 @@
 // xfb_col.cu -- instantiations and launcher of the K-COL kernels.
 #include "xfb_internal.h"
 #include "xfb_colt.cuh"
+#include "xfb_col2l.cuh"
 
 namespace xfb {
 
@@ -87,6 +88,21 @@ static int launch_colt_t(const ColParams &p, int batch, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
+// two-level K-COL (xfb_col2l.cuh): columns of 16384 points (and 4096 under XFB_COL_2L=1, an A/B and test knob)
+template <int NX, int MODE>
+static int launch_col2l_t(const ColParams &p, int batch, cudaStream_t st)
+{
+    typedef Col2LCfg<NX> C;
+    static PerDeviceInt cfg;
+    int err = 0;
+    const int resident = cfg.get([&](int *e) { return resident_ctas(col2l_kernel<NX, MODE>, C::THREADS, C::SMEM, C::TCOLS, e); }, &err);
+    if (resident <= 0) return err;
+    const int ncols = p.pitch * batch;
+    const int blocks = ncols < resident ? ncols : resident;
+    col2l_kernel<NX, MODE><<<blocks, C::THREADS, C::SMEM, st>>>(p, ncols);
+    return (int)cudaGetLastError();
+}
+
 template <int NX>
 static int launch_colt_n(int mode, const ColParams &p, int batch, cudaStream_t st)
 {
@@ -140,6 +156,13 @@ int launch_col(int nx, int mode, const ColParams &p, int batch, cudaStream_t st)
 {
     // the stepper's modes run on the TMA-staged persistent kernel (XFB_COL_GEN1=1: first-generation kernel, A/B knob)
     static const bool gen1 = env_int("XFB_COL_GEN1", 0) != 0;
+    static const bool two_level_4096 = env_int("XFB_COL_2L", 0) != 0;
+    if ((mode == COL_STEP || mode == COL_PRO) && !gen1 && p.peer_rows == 0) {
+        if (nx == 16384)
+            return mode == COL_STEP ? launch_col2l_t<16384, COL_STEP>(p, batch, st) : launch_col2l_t<16384, COL_PRO>(p, batch, st);
+        if (nx == 4096 && two_level_4096)
+            return mode == COL_STEP ? launch_col2l_t<4096, COL_STEP>(p, batch, st) : launch_col2l_t<4096, COL_PRO>(p, batch, st);
+    }
     const bool colt_only = (mode == COL_DIAG || mode == COL_FWDT || mode == COL_TSTEP || mode == COL_TPRO);
     if (colt_only && (gen1 || nx > 8192)) return (int)cudaErrorNotSupported;
     if ((mode == COL_STEP || mode == COL_PRO || colt_only) && !gen1) {

@@ -184,6 +184,17 @@ __device__ __forceinline__ void tmem_unpark8(unsigned taddr, cpx (&r)[8])
         : "r"(taddr)
         : "memory");
 }
+// 8 columns -> 4 complex registers (same waits as tmem_unpark8)
+__device__ __forceinline__ void tmem_unpark4(unsigned taddr, cpx (&r)[4])
+{
+    asm volatile(
+        "tcgen05.wait::st.sync.aligned;\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=f"(r[0].x), "=f"(r[0].y), "=f"(r[1].x), "=f"(r[1].y), "=f"(r[2].x), "=f"(r[2].y), "=f"(r[3].x), "=f"(r[3].y)
+        : "r"(taddr)
+        : "memory");
+}
 // the stores above complete asynchronously; a load of what they wrote waits for them first
 __device__ __forceinline__ void tmem_unpark(unsigned taddr, cpx (&r)[16])
 {

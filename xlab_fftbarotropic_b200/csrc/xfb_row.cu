@@ -1,6 +1,7 @@
 // xfb_row.cu -- instantiations and launcher of the K-ROW kernels.
 #include "xfb_internal.h"
 #include "xfb_rowpair.cuh"
+#include "xfb_rowpair2l.cuh"
 
 #include <cstdlib>
 
@@ -65,6 +66,33 @@ static int launch_pair_tmem(const RowParams &p, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
+// ROW_JAC for lines of 16384 points: two-level pair kernel (xfb_rowpair2l.cuh), TMA-staged and persistent.
+// XFB_ROW_2L=0 (or XFB_ROW_SINGLE=1) keeps the first-generation one-row-per-line kernel (A/B knob).
+template <int NY, bool DIST>
+static int launch_pair2l(const RowParams &p, cudaStream_t st)
+{
+    typedef Pair2LCfg<NY> C;
+    const int smem = C::smem_bytes(p.pitch);
+    constexpr int SMEM_MAX = 226 * 1024;      // 227 KB per CTA minus the kernel's static shared memory
+    if (smem > SMEM_MAX) return (int)cudaErrorInvalidValue;
+    static PerDeviceInt cfg;
+    int err = 0;
+    // the shared-memory limit is raised to the hardware maximum once per device: the staging buffer follows the pitch
+    const int resident = cfg.get([&](int *e) { return resident_ctas(rowpair2l_jac_kernel<NY, DIST>, C::THREADS, SMEM_MAX, C::TCOLS, e); }, &err);
+    if (resident <= 0) return err;
+    const int npairs = p.nrows / 2;
+    const int blocks = npairs < resident ? npairs : resident;
+    rowpair2l_jac_kernel<NY, DIST><<<blocks, C::THREADS, smem, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+static bool use_two_level_rows()
+{
+    static const bool off = (getenv("XFB_ROW_2L") && atoi(getenv("XFB_ROW_2L")) == 0) ||
+                            (getenv("XFB_ROW_SINGLE") && atoi(getenv("XFB_ROW_SINGLE")) != 0);
+    return !off;
+}
+
 static bool use_tmem_parks(int ny)
 {
     static const int forced = getenv("XFB_ROW_TMEM") ? (atoi(getenv("XFB_ROW_TMEM")) != 0 ? 1 : 0) : -1;
@@ -94,6 +122,9 @@ static int launch_row_n(int mode, const RowParams &p, cudaStream_t st)
             }
             return (int)cudaErrorInvalidValue;
         }
+    }
+    if constexpr (NY == 16384) {
+        if (mode == ROW_JAC && use_two_level_rows()) return dist ? launch_pair2l<NY, true>(p, st) : launch_pair2l<NY, false>(p, st);
     }
     switch (mode) {
     case ROW_R2C: return dist ? launch_row_t<NY, ROW_R2C, true>(p, st) : launch_row_t<NY, ROW_R2C, false>(p, st);
