@@ -156,9 +156,11 @@ int launch_col(int nx, int mode, const ColParams &p, int batch, cudaStream_t st)
 {
     // the stepper's modes run on the TMA-staged persistent kernel (XFB_COL_GEN1=1: first-generation kernel, A/B knob)
     static const bool gen1 = env_int("XFB_COL_GEN1", 0) != 0;
-    static const bool two_level_4096 = env_int("XFB_COL_2L", 0) != 0;
+    // XFB_COL_2L: 1 = two-level K-COL on 16384- and 4096-point columns, 0 = first-generation kernel at 16384 (A/B knob)
+    static const int two_level = env_int("XFB_COL_2L", -1);
+    static const bool two_level_4096 = two_level > 0;
     if ((mode == COL_STEP || mode == COL_PRO) && !gen1 && p.peer_rows == 0) {
-        if (nx == 16384)
+        if (nx == 16384 && two_level != 0)
             return mode == COL_STEP ? launch_col2l_t<16384, COL_STEP>(p, batch, st) : launch_col2l_t<16384, COL_PRO>(p, batch, st);
         if (nx == 4096 && two_level_4096)
             return mode == COL_STEP ? launch_col2l_t<4096, COL_STEP>(p, batch, st) : launch_col2l_t<4096, COL_PRO>(p, batch, st);

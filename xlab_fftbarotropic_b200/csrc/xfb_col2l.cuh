@@ -15,8 +15,10 @@
 //            y[2n] = FFT(S)[n], y[2n+1] = FFT(D)[n]  -- again the two rows of one piece: one 16-byte store.
 // One butterfly per thread in every pass (no spills); the half that waits for its transform is parked in a
 // thread-private shared-memory slot, the new stage state of the column in tensor memory (64 columns per thread).
-// Persistent CTAs walk over the columns; the pieces of the next column are pulled towards L2 while the current one is
-// transformed.
+// Persistent CTAs walk over the columns; the state blocks of the next column are pulled towards L2 while the current one
+// is transformed.  What bounds it (profiles/r02_16384_*): a one-column tile moves 16-byte pieces, one 32-byte sector per
+// lane -- 1280 fully divergent load/store instructions per column next to the shared-memory exchanges of ten 8192-point
+// transforms in the same load/store unit.
 #pragma once
 #include "xfb_col.cuh"
 #include "xfb_row.cuh"      // w32()
@@ -71,13 +73,20 @@ col2l_kernel(const ColParams p, const int ncols)
         const size_t piece0 = moff + (size_t)jl * 2;
         const size_t pstride = (size_t)p.pitch * 2;
         {
-            // the next column of this CTA towards L2 (its pieces, and the state blocks where they are contiguous)
+            // the epilogue operands of this CTA's NEXT column towards L2: with a tile width of one the column's block of
+            // each state array is contiguous, three bulk prefetches.  (16384^2, per launch: 6.43 ms without, 5.42 ms with;
+            // pulling the column's 8192 scattered 16-byte pieces of the tendency in as well -- one prefetch instruction
+            // each -- costs more load/store-unit time than it saves: 5.46 ms.)
             const int nc = col + gridDim.x;
-            if (nc < ncols && MODE == COL_STEP) {
+            if (nc < ncols && MODE == COL_STEP && p.st_row_stride == 1) {
                 const int nm = nc / p.pitch, njl = nc - nm * p.pitch;
-                const cpx *nsrc = p.jint + (size_t)nm * (size_t)p.member_stride + (size_t)njl * 2;
-#pragma unroll 4
-                for (int k = 0; k < 16; ++k) prefetch_l2(nsrc + (size_t)(t + k * G) * pstride);
+                const size_t ns0 = (size_t)nm * (size_t)p.member_stride + (size_t)njl * (size_t)p.st_tile_stride;
+                constexpr unsigned bytes = NX * (unsigned)sizeof(cpx);
+                if (t == 0) bulk_prefetch_l2(p.z0 + ns0, bytes);
+                if (p.stage != 1) {
+                    if (t == 32) bulk_prefetch_l2(p.zk + ns0, bytes);
+                    if (t == 64) bulk_prefetch_l2(p.acc + ns0, bytes);
+                }
             }
         }
         cpx v[1][16];
