@@ -49,7 +49,7 @@ def dt_for(n: int) -> float:
 
 def measured_traffic(grid: int, which: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture, or None"""
-    p = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         d = json.load(open(p))
         return float(d[str(grid)][which]["dram_bytes_per_launch"]), d["source"]
@@ -395,8 +395,8 @@ def gpu_arm(args):
     achieved = col_gbs if dominant == "col" else row_gbs
     step_gbs = ALGO_BYTES_PER_PT_STEP * value / world / 1e9
     traffic, traffic_src = measured_traffic(n, "col_step" if dominant == "col" else "row_jac") if args.members == 1 else (None, None)
-    names = {"col": "colt_kernel<COL_STEP>" if n <= 8192 else "col_kernel<COL_STEP>",
-             "row": ("rowpair_jac_tmem_kernel" if n == 8192 else "rowpair_kernel<ROW_JAC>") if n <= 8192 else "row_kernel<ROW_JAC>"}
+    names = {"col": "colt_kernel<COL_STEP>" if n <= 8192 else "col2l_kernel<COL_STEP>",
+             "row": ("rowpair_jac_tmem_kernel" if n >= 4096 else "rowpair_kernel<ROW_JAC>") if n <= 8192 else "rowpair2l_jac_kernel"}
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "traffic_source": traffic_src, "kernel": names[dominant],

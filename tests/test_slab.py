@@ -252,3 +252,26 @@ def test_loopback_diagnostics_and_keff_histograms():
     assert rel_l2(team.get_field(xfb.capi.VORT), one.get_field(xfb.capi.VORT)) < 2e-6
     one.close()
     team.close()
+
+
+@pytest.mark.gpu
+def test_loopback_16384_two_level_kernels():
+    """the slab path at the grid bench.py measures (BASELINE.json configs[4]): two-level K-ROW fed by one bulk copy per
+    panel, two-level K-COL storing this rank's own row pairs straight into its receive arrays (no self-copy in the
+    exchange) -- against the single-GPU path, bit for bit (same kernels, same arithmetic)"""
+    import xlab_fftbarotropic_b200 as xfb
+    n, p, c = 16384, 2, 4
+    x = (np.arange(n, dtype=np.float32) / n)
+    v0 = (5e-3 * np.exp(-((x[:, None] - 0.5) / 0.07) ** 2 - ((x[None, :] - 0.45) / 0.04) ** 2)).astype(np.float32)
+    one = xfb.Backend(n)
+    one.set_vorticity(v0)
+    one.step(2, 0.25)
+    ref = one.get_field(xfb.capi.VORT)
+    one.close()
+    team = xfb.LoopbackTeam(n, p, c)
+    team.set_vorticity(v0)
+    team.step(2, 0.25)
+    got = team.get_field(xfb.capi.VORT)
+    team.close()
+    assert np.isfinite(got).all()
+    assert rel_l2(got, ref) < 2e-6, rel_l2(got, ref)

@@ -27,6 +27,13 @@ int col_tile_width(int nx)
     }
 }
 
+bool col_two_level(int nx)
+{
+    static const bool gen1 = env_int("XFB_COL_GEN1", 0) != 0;
+    static const int two_level = env_int("XFB_COL_2L", -1);
+    return !gen1 && ((nx == 16384 && two_level != 0) || (nx == 4096 && two_level > 0));
+}
+
 // ---- tensor maps for the TMA tiles of colt_kernel ------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -98,7 +105,11 @@ static int launch_col2l_t(const ColParams &p, int batch, cudaStream_t st)
     const int resident = cfg.get([&](int *e) { return resident_ctas(col2l_kernel<NX, MODE>, C::THREADS, C::SMEM, C::TCOLS, e); }, &err);
     if (resident <= 0) return err;
     const int ncols = p.pitch * batch;
-    const int blocks = ncols < resident ? ncols : resident;
+    int blocks = ncols < resident ? ncols : resident;
+    // slab runs with the SM push kernel: a persistent grid on every SM would keep the push CTAs of the previous chunk
+    // waiting until this launch ends; a few SMs are left to them (XFB_SLAB_SPARE_SMS)
+    static const int spare = env_int("XFB_SLAB_SPARE_SMS", 8);      // 2 GPUs, 16384^2: 0 -> 19.25, 8 -> 18.72, 16 -> 18.89, 32 -> 20.58 ms per step
+    if (p.self_pieces > 0 && blocks > 2 * spare) blocks -= spare;
     col2l_kernel<NX, MODE><<<blocks, C::THREADS, C::SMEM, st>>>(p, ncols);
     return (int)cudaGetLastError();
 }
@@ -157,13 +168,10 @@ int launch_col(int nx, int mode, const ColParams &p, int batch, cudaStream_t st)
     // the stepper's modes run on the TMA-staged persistent kernel (XFB_COL_GEN1=1: first-generation kernel, A/B knob)
     static const bool gen1 = env_int("XFB_COL_GEN1", 0) != 0;
     // XFB_COL_2L: 1 = two-level K-COL on 16384- and 4096-point columns, 0 = first-generation kernel at 16384 (A/B knob)
-    static const int two_level = env_int("XFB_COL_2L", -1);
-    static const bool two_level_4096 = two_level > 0;
-    if ((mode == COL_STEP || mode == COL_PRO) && !gen1 && p.peer_rows == 0) {
-        if (nx == 16384 && two_level != 0)
+    if ((mode == COL_STEP || mode == COL_PRO) && p.peer_rows == 0 && col_two_level(nx)) {
+        if (nx == 16384)
             return mode == COL_STEP ? launch_col2l_t<16384, COL_STEP>(p, batch, st) : launch_col2l_t<16384, COL_PRO>(p, batch, st);
-        if (nx == 4096 && two_level_4096)
-            return mode == COL_STEP ? launch_col2l_t<4096, COL_STEP>(p, batch, st) : launch_col2l_t<4096, COL_PRO>(p, batch, st);
+        return mode == COL_STEP ? launch_col2l_t<4096, COL_STEP>(p, batch, st) : launch_col2l_t<4096, COL_PRO>(p, batch, st);
     }
     const bool colt_only = (mode == COL_DIAG || mode == COL_FWDT || mode == COL_TSTEP || mode == COL_TPRO);
     if (colt_only && (gen1 || nx > 8192)) return (int)cudaErrorNotSupported;

@@ -57,6 +57,11 @@ struct ColParams {
     // [R * peer_rows, (R + 1) * peer_rows); peer_out[R * 4 + f] points at the block of receive array f of rank R that
     // holds THIS rank's column chunks, peer_chunk_off selects the chunk of this launch; inside the block the rows are in
     // the pair layout with pitch `pitch` (= columns per chunk).
+    // slab-decomposed runs, two-level kernel (xfb_col2l.cuh): the 16-byte pieces [self_piece0, self_piece0 + self_pieces) of a
+    // column -- the row pairs this rank owns itself -- go straight into this rank's own receive arrays (self_out[f] points
+    // at the block of this launch's chunk), so the exchange has no self-copy to do; self_pieces == 0: everything to t_out
+    int self_piece0, self_pieces;
+    cpx *self_out[4];
     int peer_rows;        // 0: local output
     int peer_rows_shift;  // log2(peer_rows)
     long long peer_chunk_off;

@@ -243,11 +243,15 @@ col2l_kernel(const ColParams p, const int ncols)
             }
             col_fft<H, 1, 1>(v, F, tt, cc, tw);
             cpx *dst = p.t_out[f] + piece0;
+            cpx *dself = p.self_out[f] + (size_t)jl * 2;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const cpx e = park[k * G + t];
-                // rows 2m, 2m+1 of piece m = t + k G, un-swapped
-                *reinterpret_cast<float4 *>(dst + (size_t)(tl + k * G) * pstride) = make_float4(e.y, e.x, v[0][k].y, v[0][k].x);
+                // rows 2m, 2m+1 of piece m = t + k G, un-swapped; this rank's own row pairs (slab runs) skip the exchange
+                const int m = tl + k * G;
+                const unsigned ms = (unsigned)(m - p.self_piece0);
+                float4 *o = reinterpret_cast<float4 *>(ms < (unsigned)p.self_pieces ? dself + (size_t)ms * pstride : dst + (size_t)m * pstride);
+                *o = make_float4(e.y, e.x, v[0][k].y, v[0][k].x);
             }
         }
     }

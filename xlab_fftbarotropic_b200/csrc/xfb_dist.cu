@@ -99,6 +99,9 @@ enum { ROW2COL = 0, COL2ROW = 1 };
 // (array 0 of the block = jint_recv).  Panel (q, c) of rank `me` lands at rows [me * rows, ...) of chunk c there.
 static int build_panel_table(xfb_handle h, cpx *const *recv_of_rank)
 {
+    // two-level K-COL (16384-point columns): its own row pairs go straight into this rank's receive arrays
+    static const bool self_off = getenv("XFB_SLAB_SELF_DIRECT") && atoi(getenv("XFB_SLAB_SELF_DIRECT")) == 0;
+    h->self_direct = !self_off && col_two_level(h->nx) && (h->rows / 2) % (h->nx / 32) == 0;
     static const bool off = getenv("XFB_SLAB_FUSED") && atoi(getenv("XFB_SLAB_FUSED")) == 0;
     if (off) return 0;
     const int n = h->nranks * h->nchunks;
@@ -155,8 +158,9 @@ __global__ void __launch_bounds__(512) push_kernel(const PushSegs s)
 // One all-to-all of the blocks (column chunks [c0, c1), local rows [r0, r1)) of `na` arrays.
 // NCCL: issued for the single local rank on `st`.  Loopback: device copies for every rank on the shared stream.
 static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *col_ptrs_of_rank, int na, int c0, int c1, int r0,
-                    int r1, cudaStream_t st)
+                    int r1, cudaStream_t st, bool skip_self = false)
 {
+    // skip_self: the producer has already put every rank's own block in place (two-level K-COL, ColParams::self_out)
     // row_ptrs_of_rank / col_ptrs_of_rank: [nlocal][na]
     xfb_handle h0 = T->local[0];
     const size_t count = (size_t)(r1 - r0) * h0->pitch;      // complex elements per block
@@ -165,6 +169,7 @@ static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *
             for (int q = 0; q < T->nranks; ++q)
                 for (int a = 0; a < na; ++a)
                     for (int c = c0; c < c1; ++c) {
+                        if (skip_self && q == R) continue;
                         cpx *rowR = row_ptrs_of_rank[R * na + a], *colR = col_ptrs_of_rank[R * na + a];
                         cpx *rowq = row_ptrs_of_rank[q * na + a], *colq = col_ptrs_of_rank[q * na + a];
                         if (dir == ROW2COL)
@@ -202,7 +207,7 @@ static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *
                 segs.n = 0;
                 return 0;
             };
-            for (int i = 0; i < T->nranks; ++i) {
+            for (int i = skip_self ? 1 : 0; i < T->nranks; ++i) {
                 const int q = (me + i) % T->nranks;
                 cpx *peer = h0->peer_recv[q];
                 for (int c = c0; c < c1; ++c) {
@@ -223,7 +228,7 @@ static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *
         const int pieces = (T->nranks - 1 >= ncs) ? 1 : ncs / (T->nranks - 1);
         const size_t piece_elems = ((count + pieces - 1) / pieces + 1) & ~(size_t)1;      // even: 16-byte aligned pieces
         int slot = 0;
-        for (int i = 0; i < T->nranks; ++i) {
+        for (int i = skip_self ? 1 : 0; i < T->nranks; ++i) {
             const int q = (me + i) % T->nranks;
             cpx *peer = h0->peer_recv[q];
             for (int pc = 0; pc < pieces; ++pc) {
@@ -281,7 +286,7 @@ static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *
                 NCK(g_nccl.Recv(recvp, 2 * count, ncclFloat, q, T->comm, st));
             }
     NCK(g_nccl.GroupEnd());
-    for (int a = 0; a < na; ++a)
+    for (int a = 0; a < na && !skip_self; ++a)
         for (int c = c0; c < c1; ++c) {
             cpx *row = row_ptrs_of_rank[a] + row_off(h0, me, c, r0), *col = col_ptrs_of_rank[a] + col_off(h0, me, c, r0);
             CK(cudaMemcpyAsync((dir == ROW2COL) ? col : row, (dir == ROW2COL) ? row : col, sizeof(cpx) * count,
@@ -318,6 +323,11 @@ static int launch_col_chunk(xfb_handle h, int mode, int chunk, int stage, float 
     if (mode == COL_INV) { c.inv_in = inv_in + off; c.t_out[0] = inv_out + off; }
     c.dt = dt; c.stage = stage;
     c.dt_stage = (stage == 3) ? dt : dt / 2.0f;          // main.cpp:296,299,302
+    if (h->self_direct && (mode == COL_STEP || mode == COL_PRO)) {
+        c.self_piece0 = h->rank * (h->rows / 2);
+        c.self_pieces = h->rows / 2;
+        for (int f = 0; f < 4; ++f) c.self_out[f] = h->tr[f] + row_off(h, h->rank, chunk, 0);
+    }
     if (h->fused_col && mode != COL_FWD) {
         c.peer_rows = h->rows;
         c.peer_rows_shift = 0;
@@ -409,7 +419,7 @@ static int rows_then_exchange(Team *T, F produce, GR row_of, GC col_of)
 // x pass for all local ranks (column chunks) + exchange of `na` arrays back to the row side.
 //   produce(h, chunk) launches K-COL ; col_of(h, a) / row_of(h, a) name array a on the two sides
 template <typename F, typename GC, typename GR>
-static int cols_then_exchange(Team *T, F produce, GC col_of, GR row_of, int na)
+static int cols_then_exchange(Team *T, F produce, GC col_of, GR row_of, int na, bool skip_self = false)
 {
     xfb_handle h0 = T->local[0];
     const int C = h0->nchunks;
@@ -433,14 +443,14 @@ static int cols_then_exchange(Team *T, F produce, GC col_of, GR row_of, int na)
         for (int l = 0; l < T->nlocal; ++l)
             for (int c = 0; c < C; ++c)
                 if (int e = produce(T->local[l], c)) return e;
-        return exchange(T, COL2ROW, rp, cp, na, 0, C, 0, h0->rows, h0->stream);
+        return exchange(T, COL2ROW, rp, cp, na, 0, C, 0, h0->rows, h0->stream, skip_self);
     }
     for (int c = 0; c < C; ++c) {
         if (int e = produce(h0, c)) return e;
         CK(cudaEventRecord(h0->ev_chunk[c], h0->stream));
         CK(cudaStreamWaitEvent(h0->comm_stream, h0->ev_chunk[c], 0));
         a2a_mark(h0, h0->comm_stream);
-        if (int e = exchange(T, COL2ROW, rp, cp, na, c, c + 1, 0, h0->rows, h0->comm_stream)) return e;
+        if (int e = exchange(T, COL2ROW, rp, cp, na, c, c + 1, 0, h0->rows, h0->comm_stream, skip_self)) return e;
         a2a_mark(h0, h0->comm_stream);
     }
     if (int e = phase_barrier(T, h0->comm_stream)) return e;
@@ -476,7 +486,7 @@ static int team_products(Team *T, int mode, int stage, float dt)
 {
     return cols_then_exchange(
         T, [&](xfb_handle h, int c) { return launch_col_chunk(h, mode, c, stage, dt, nullptr, nullptr); },
-        [](xfb_handle h, int a) { return h->t[a]; }, [](xfb_handle h, int a) { return h->tr[a]; }, 4);
+        [](xfb_handle h, int a) { return h->t[a]; }, [](xfb_handle h, int a) { return h->tr[a]; }, 4, T->local[0]->self_direct);
 }
 
 static int team_step(Team *T, int nsteps, float dt)

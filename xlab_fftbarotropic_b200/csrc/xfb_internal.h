@@ -11,6 +11,8 @@ namespace xfb {
 
 // column tile width used for a given x length (0 = size not served by the fused kernels)
 int col_tile_width(int nx);
+// true if the stepper's K-COL for this x length is the two-level kernel (xfb_col2l.cuh)
+bool col_two_level(int nx);
 bool row_size_ok(int ny);
 
 // returns cudaError_t as int
