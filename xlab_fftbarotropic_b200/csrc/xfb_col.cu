@@ -104,13 +104,16 @@ static int launch_col2l_t(const ColParams &p, int batch, cudaStream_t st)
     int err = 0;
     const int resident = cfg.get([&](int *e) { return resident_ctas(col2l_kernel<NX, MODE>, C::THREADS, C::SMEM, C::TCOLS, e); }, &err);
     if (resident <= 0) return err;
+    CUtensorMap jmap = CUtensorMap();
+    if (MODE == COL_STEP)      // one-column boxes of the tendency: 2 elements (one 16-byte piece) x BOXR row pairs
+        if (int e = make_pair_map(&jmap, p.jint, (long long)NX * batch, p.pitch, 1, C::BOXR)) return e;
     const int ncols = p.pitch * batch;
     int blocks = ncols < resident ? ncols : resident;
     // slab runs with the SM push kernel: a persistent grid on every SM would keep the push CTAs of the previous chunk
     // waiting until this launch ends; a few SMs are left to them (XFB_SLAB_SPARE_SMS)
     static const int spare = env_int("XFB_SLAB_SPARE_SMS", 8);      // 2 GPUs, 16384^2: 0 -> 19.25, 8 -> 18.72, 16 -> 18.89, 32 -> 20.58 ms per step
     if (p.self_pieces > 0 && blocks > 2 * spare) blocks -= spare;
-    col2l_kernel<NX, MODE><<<blocks, C::THREADS, C::SMEM, st>>>(p, ncols);
+    col2l_kernel<NX, MODE><<<blocks, C::THREADS, C::SMEM, st>>>(p, jmap, ncols);
     return (int)cudaGetLastError();
 }
 

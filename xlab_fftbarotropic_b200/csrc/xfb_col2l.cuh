@@ -20,6 +20,8 @@
 // lane -- 1280 fully divergent load/store instructions per column next to the shared-memory exchanges of ten 8192-point
 // transforms in the same load/store unit.
 #pragma once
+#include <cuda.h>
+
 #include "xfb_col.cuh"
 #include "xfb_row.cuh"      // w32()
 
@@ -32,22 +34,76 @@ struct Col2LCfg {
     static constexpr int THREADS = G;
     static constexpr int F_BYTES = LinePlan<H>::PADDED * (int)sizeof(cpx);
     static constexpr int PARK_BYTES = H * (int)sizeof(cpx);
-    static constexpr int SMEM = F_BYTES + PARK_BYTES;
-    static constexpr int TCOLS = (THREADS / 128) * 64 < 32 ? 32 : (THREADS / 128) * 64;
+    // the NEXT column of the tendency is streamed in through a ring of TMA boxes while the current one is transformed
+    static constexpr int BOXR = (G >= 256) ? 256 : G;                 // row pairs per TMA box (a box row = one 16-byte piece)
+    static constexpr int NB = G / BOXR;                              // boxes per ring slot: a slot = one piece of every thread
+    static constexpr int SLOT_BYTES = G * 16;
+    static constexpr int RING_SLOTS = 3;
+    static constexpr int SMEM = F_BYTES + PARK_BYTES + RING_SLOTS * SLOT_BYTES + 128;      // + alignment slack
+    static constexpr int TCOLS = (THREADS / 128) * 128;               // per thread: 64 columns of stage state + 64 of incoming column
     static_assert(THREADS % 128 == 0 && THREADS <= 512, "col2l: NX / 32 threads, whole groups of four warps");
 };
 
 // exp(-2 pi i (t + k G) / NX) = wt * exp(-2 pi i k / 32)   (G = NX / 32)
 __device__ __forceinline__ cpx col2l_tw(const cpx wt, const int k) { return (k == 0) ? wt : cmul(wt, w32(k)); }
 
+// Streaming of the next column into tensor memory.  Ring slot q of a column = pieces [q G, q G + G): exactly ONE piece
+// (rows 2m, 2m+1) of every thread, its k = q.  The hook of col_fft calls step() at two barrier-separated points of each of
+// the eight inverse transforms of a column = 16 points: thread 0 issues the TMA loads of slot q + 2 into the buffer slot
+// q - 1 left, every thread waits for slot q and copies its piece into its TMEM lane (E[q] and O[q]).  A one-column tile
+// has 16-byte box rows -- the TMA engine's slow case (profiles/r01_probe_tma_tile.txt) -- but one column per ~80 us is
+// 1 % of even that rate, it costs no load/store-unit time and no thread ever waits for it.
+template <int NX>
+struct Col2LRing {
+    typedef Col2LCfg<NX> C;
+    const CUtensorMap *map;
+    unsigned char *ring;
+    unsigned long long *bar;
+    unsigned tin;         // this thread's incoming TMEM region: E[k] at + 2k, O[k] at + 32 + 2k
+    int cx, cy;           // TMA coordinates of piece 0 of the column being streamed in
+    int q;                // next slot of that column to consume; >= 16: nothing to do
+    int slot;
+    unsigned parity;
+
+    __device__ __forceinline__ void issue(const int qq, const int sl) const      // thread 0
+    {
+        mbar_expect_tx(bar + sl, (unsigned)C::SLOT_BYTES);
+#pragma unroll
+        for (int b = 0; b < C::NB; ++b)
+            tma_load_2d(ring + (size_t)sl * C::SLOT_BYTES + (size_t)b * C::BOXR * 16, map, cx, cy + qq * C::G + b * C::BOXR, bar + sl);
+    }
+    __device__ __forceinline__ void begin(const int x, const int y)
+    {
+        cx = x; cy = y; q = 0;
+        if (threadIdx.x == 0) {
+            issue(0, slot);
+            issue(1, slot == 2 ? 0 : slot + 1);
+        }
+    }
+    __device__ __forceinline__ void step()
+    {
+        if (q >= 16) return;
+        if (threadIdx.x == 0 && q + 2 < 16) issue(q + 2, slot == 0 ? 2 : slot - 1);      // (slot + 2) mod 3
+        mbar_wait(bar + slot, parity);
+        const float4 x = *reinterpret_cast<const float4 *>(ring + (size_t)slot * C::SLOT_BYTES + (size_t)threadIdx.x * 16);
+        tmem_park1(tin + (unsigned)(2 * q), mk(x.x, x.y));              // row 2m   -> E
+        tmem_park1(tin + (unsigned)(32 + 2 * q), mk(x.z, x.w));         // row 2m+1 -> O
+        ++q;
+        if (slot == 2) { slot = 0; parity ^= 1u; } else ++slot;
+    }
+    __device__ __forceinline__ void operator()(const int e, const bool) { if (e < 2) step(); }
+};
+
 template <int NX, int MODE>
 __global__ void __launch_bounds__(Col2LCfg<NX>::THREADS, 1)
-col2l_kernel(const ColParams p, const int ncols)
+col2l_kernel(const ColParams p, const __grid_constant__ CUtensorMap jmap, const int ncols)
 {
     typedef Col2LCfg<NX> C;
     constexpr int H = C::H, G = C::G;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem_raw = smem_dyn + ((128 - (smem_u32(smem_dyn) & 127)) & 127);       // TMA needs 128-byte aligned shared addresses
     __shared__ unsigned tmem_slot;
+    __shared__ unsigned long long ring_bar[C::RING_SLOTS];
     cpx *F = reinterpret_cast<cpx *>(smem_raw);
     cpx *park = reinterpret_cast<cpx *>(smem_raw + C::F_BYTES);      // park[k * G + t]: thread-private, conflict-free
 
@@ -56,10 +112,30 @@ col2l_kernel(const ColParams p, const int ncols)
     LineTw<H> tw[1];
     tw[0].init(p.tw, p.twn, t);
     const cpx wt = __ldg(p.tw + (size_t)t * (p.twn / NX));
-    const unsigned tbase = tmem_alloc_cta<C::TCOLS>(&tmem_slot);
+    if (t == 0) {
+        for (int i = 0; i < C::RING_SLOTS; ++i) mbar_init(&ring_bar[i], 1);
+        mbar_fence_init();
+    }
+    const unsigned tbase = tmem_alloc_cta<C::TCOLS>(&tmem_slot);       // includes a CTA barrier
     const int warp = t >> 5;
-    const unsigned tkeep = tbase + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 64);   // lo: +0..31, hi: +32..63
+    const unsigned tkeep = tbase + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 128);  // lo: +0..31, hi: +32..63
     const size_t srow = (size_t)p.st_row_stride;                      // = tile width of the state arrays
+    Col2LRing<NX> rs;
+    rs.map = &jmap;
+    rs.ring = smem_raw + C::F_BYTES + C::PARK_BYTES;
+    rs.bar = ring_bar;
+    rs.tin = tkeep + 64u;
+    rs.slot = 0; rs.parity = 0; rs.q = 16; rs.cx = 0; rs.cy = 0;
+    if (MODE == COL_STEP && (int)blockIdx.x < ncols) {
+        // the CTA's first column: streamed into tensor memory with nothing to hide behind
+        const int member = (int)blockIdx.x / p.pitch, jl = (int)blockIdx.x - member * p.pitch;
+        rs.begin(jl * 2, member * (NX / 2));
+#pragma unroll 1
+        for (int b = 0; b < 16; ++b) {
+            rs.step();
+            __syncthreads();
+        }
+    }
 
     for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
         const int member = col / p.pitch, jl = col - member * p.pitch;
@@ -93,24 +169,32 @@ col2l_kernel(const ColParams p, const int ncols)
 
         if (MODE == COL_STEP) {
             // ------------------------------------------------------------ forward (decimation in time) + epilogue
-            const cpx *src = p.jint + piece0;
-            {
-                // all sixteen pieces in flight at once (one latency exposure; the registers are free at this point)
-                float4 x[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) x[k] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)(t + k * G) * pstride));
+            for (int h = 0; h < 2; ++h) {                    // E = the rows 2m of this thread's sixteen pieces (streamed in earlier)
+                cpx a[8];
+                tmem_unpark8(rs.tin + (unsigned)(16 * h), a);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    v[0][k] = mk(x[k].x, x[k].y);                            // row 2m   -> E
-                    park[k * G + t] = mk(x[k].z, x[k].w);                    // row 2m+1 -> O, waits in its slot
-                }
+                for (int q = 0; q < 8; ++q) v[0][8 * h + q] = a[q];
             }
             col_fft<H, 1, 1>(v, F, tt, cc, tw);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {                   // E into the slot, O out of it
-                const cpx o = park[k * G + t];
-                park[k * G + t] = v[0][k];
-                v[0][k] = o;
+            for (int k = 0; k < 16; ++k) park[k * G + t] = v[0][k];          // E waits in the slot
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                    // O = the rows 2m+1
+                cpx a[8];
+                tmem_unpark8(rs.tin + (unsigned)(32 + 16 * h), a);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[0][8 * h + q] = a[q];
+            }
+            {
+                // the incoming region is free: the next column of this CTA streams into it under the inverse transforms
+                const int nc = col + gridDim.x;
+                if (nc < ncols) {
+                    const int nm = nc / p.pitch, njl = nc - nm * p.pitch;
+                    rs.begin(njl * 2, nm * (NX / 2));
+                } else {
+                    rs.q = 16;
+                }
             }
             // epilogue operands (z0, zk, acc) travel in quarters of four rows, one quarter ahead of the arithmetic; the first
             // quarter is requested inside the second transform, before its last exchange
@@ -234,14 +318,14 @@ col2l_kernel(const ColParams p, const int ncols)
                     park[k * G + t] = cmul(csub(a, b), col2l_tw(wl, k));        // D, waits in the slot
                 }
             }
-            col_fft<H, 1, 1>(v, F, tt, cc, tw);
+            col_fft<H, 1, 1, Col2LRing<NX>>(v, F, tt, cc, tw, false, rs);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {                   // rows 2m into the slot, D out of it
                 const cpx d = park[k * G + t];
                 park[k * G + t] = v[0][k];
                 v[0][k] = d;
             }
-            col_fft<H, 1, 1>(v, F, tt, cc, tw);
+            col_fft<H, 1, 1, Col2LRing<NX>>(v, F, tt, cc, tw, false, rs);
             cpx *dst = p.t_out[f] + piece0;
             cpx *dself = p.self_out[f] + (size_t)jl * 2;
 #pragma unroll
