@@ -112,7 +112,12 @@ static int launch_col2l_t(const ColParams &p, int batch, cudaStream_t st)
     // slab runs with the SM push kernel: a persistent grid on every SM would keep the push CTAs of the previous chunk
     // waiting until this launch ends; a few SMs are left to them (XFB_SLAB_SPARE_SMS)
     static const int spare = env_int("XFB_SLAB_SPARE_SMS", 8);      // 2 GPUs, 16384^2: 0 -> 19.25, 8 -> 18.72, 16 -> 18.89, 32 -> 20.58 ms per step
-    if (p.self_pieces > 0 && blocks > 2 * spare) blocks -= spare;
+    if (p.self_pieces > 0 && resident > 2 * spare) {
+        // ... unless that costs a whole extra wave of columns (8 GPUs: 132 columns per chunk on 140 CTAs is one wave, on
+        // 124 it is two -- 5.8 -> 7.9 ms per step)
+        const int fewer = resident - spare;
+        if ((ncols + fewer - 1) / fewer == (ncols + resident - 1) / resident) blocks = ncols < fewer ? ncols : fewer;
+    }
     col2l_kernel<NX, MODE><<<blocks, C::THREADS, C::SMEM, st>>>(p, jmap, ncols);
     return (int)cudaGetLastError();
 }

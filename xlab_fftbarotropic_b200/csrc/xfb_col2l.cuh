@@ -100,8 +100,9 @@ col2l_kernel(const ColParams p, const __grid_constant__ CUtensorMap jmap, const 
 {
     typedef Col2LCfg<NX> C;
     constexpr int H = C::H, G = C::G;
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char *smem_raw = smem_dyn + ((128 - (smem_u32(smem_dyn) & 127)) & 127);       // TMA needs 128-byte aligned shared addresses
+    // TMA needs 128-byte aligned shared addresses: the declared alignment makes every offset below a link-time constant
+    // (an alignment computed at run time costs registers that the transforms then spill)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned tmem_slot;
     __shared__ unsigned long long ring_bar[C::RING_SLOTS];
     cpx *F = reinterpret_cast<cpx *>(smem_raw);
@@ -126,17 +127,6 @@ col2l_kernel(const ColParams p, const __grid_constant__ CUtensorMap jmap, const 
     rs.bar = ring_bar;
     rs.tin = tkeep + 64u;
     rs.slot = 0; rs.parity = 0; rs.q = 16; rs.cx = 0; rs.cy = 0;
-    if (MODE == COL_STEP && (int)blockIdx.x < ncols) {
-        // the CTA's first column: streamed into tensor memory with nothing to hide behind
-        const int member = (int)blockIdx.x / p.pitch, jl = (int)blockIdx.x - member * p.pitch;
-        rs.begin(jl * 2, member * (NX / 2));
-#pragma unroll 1
-        for (int b = 0; b < 16; ++b) {
-            rs.step();
-            __syncthreads();
-        }
-    }
-
     for (int col = blockIdx.x; col < ncols; col += gridDim.x) {
         const int member = col / p.pitch, jl = col - member * p.pitch;
         const size_t moff = (size_t)member * (size_t)p.member_stride;
@@ -169,8 +159,25 @@ col2l_kernel(const ColParams p, const __grid_constant__ CUtensorMap jmap, const 
 
         if (MODE == COL_STEP) {
             // ------------------------------------------------------------ forward (decimation in time) + epilogue
+            if (col == (int)blockIdx.x) {
+                // the CTA's first column has nothing to hide a stream behind (a slab chunk may hold a single column per
+                // CTA, and a one-column TMA box moves 16-byte rows at a crawl): its sixteen pieces come with one burst of
+                // 16-byte loads and take the same way through tensor memory as the streamed columns
+                const cpx *src = p.jint + piece0;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {                    // E = the rows 2m of this thread's sixteen pieces (streamed in earlier)
+                for (int h = 0; h < 2; ++h) {
+                    float4 x[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) x[q] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)(t + (8 * h + q) * G) * pstride));
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        tmem_park1(rs.tin + (unsigned)(2 * (8 * h + q)), mk(x[q].x, x[q].y));            // row 2m   -> E
+                        tmem_park1(rs.tin + (unsigned)(32 + 2 * (8 * h + q)), mk(x[q].z, x[q].w));       // row 2m+1 -> O
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                    // E = the rows 2m of this thread's sixteen pieces
                 cpx a[8];
                 tmem_unpark8(rs.tin + (unsigned)(16 * h), a);
 #pragma unroll
