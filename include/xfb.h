@@ -120,8 +120,9 @@ int xfb_get_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cma
  * uses that stage's velocity, the tendency is dealiased and combined exactly like the vorticity's
  * (src/main.cpp:225-251,286-312 with c for vort and kappa for NU), so a tracer equal to the vorticity with
  * kappa == nu and no forcing stays bit-identical to it.  `tracer` is nx*ny floats, host or device; kappa is one value
- * per handle (the last call's).  Single-GPU handles: power-of-two grids <= 8192 (fused kernels) and the generic
- * mixed-radix sizes (e.g. 768); XFB_E_SIZE for 16384 and slab-decomposed handles.
+ * per handle (the last call's).  Power-of-two grids 256 .. 16384 (fused kernels), the generic mixed-radix sizes (e.g. 768) and
+ * slab-decomposed handles (`tracer` = the LOCAL rows, collective; the tracer's tendency and its two gradient products
+ * travel through three more receive arrays of the same CUDA-IPC block).
  * Read back with xfb_get_field(..., XFB_TRACER, ...); effective-diffusivity histograms over the tracer: */
 int xfb_set_tracer(xfb_handle h, int member, const float *tracer, float kappa);
 int xfb_get_tracer_keff_hist(xfb_handle h, int member, int nbins, float cmin, float cmax, double *area, double *grad2);
@@ -160,6 +161,7 @@ int xfb_loopback_create(xfb_loopback *t, int nx, int ny, float lx, float ly, flo
 int xfb_loopback_destroy(xfb_loopback t);
 int xfb_loopback_set_vorticity(xfb_loopback t, const float *vort);
 int xfb_loopback_set_source(xfb_loopback t, const float *src);
+int xfb_loopback_set_tracer(xfb_loopback t, const float *tracer, float kappa);
 int xfb_loopback_step(xfb_loopback t, int nsteps, float dt);
 int xfb_loopback_get_field(xfb_loopback t, int which, float *out);
 int xfb_loopback_get_diagnostics(xfb_loopback t, float *tfil, float *deform);

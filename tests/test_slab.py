@@ -170,9 +170,12 @@ def test_loopback_team_matches_single_gpu(n, p, c):
     for which in (xfb.capi.VORT, xfb.capi.PSI, xfb.capi.U, xfb.capi.V, xfb.capi.DEFORM):
         a, b = one.get_field(which), team.get_field(which)
         # the deformation factor is a ratio of differences of second derivatives, formed by the fused float32
-        # multipliers on one GPU and by the operator tables on the slab path: a looser bound than the state fields
-        tol = 2e-5 if which == xfb.capi.DEFORM else 2e-6
-        assert rel_l2(b, a) < tol and np.abs(a - b).max() <= 10 * tol * np.abs(a).max(), f"field {which}: {rel_l2(b, a)}"
+        # multipliers on one GPU and by the operator tables on the slab path: north_star's 1e-5 instead of the 2e-6
+        # asked of the state fields (pointwise it is a ratio of small numbers where the flow is at rest)
+        tol = 1e-5 if which == xfb.capi.DEFORM else 2e-6
+        assert rel_l2(b, a) < tol, f"field {which}: {rel_l2(b, a)}"
+        if which != xfb.capi.DEFORM:
+            assert np.abs(a - b).max() <= 10 * tol * np.abs(a).max(), f"field {which}"
     # stepping again after the record fields were taken (the prologue is redone)
     one.step(1, 3.0)
     team.step(1, 3.0)
@@ -274,4 +277,32 @@ def test_loopback_16384_two_level_kernels():
     got = team.get_field(xfb.capi.VORT)
     team.close()
     assert np.isfinite(got).all()
+    assert rel_l2(got, ref) < 2e-6, rel_l2(got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p,c", [(512, 2, 2), (1024, 4, 1)])
+def test_loopback_passive_tracer(n, p, c):
+    """the passive tracer on slab handles: its tendency and its two gradient products cross the ranks through three more
+    receive arrays; (i) a tracer equal to the vorticity with kappa = nu stays bit-identical to the vorticity the same team
+    computes, (ii) an independent tracer matches the single-GPU tracer"""
+    import xlab_fftbarotropic_b200 as xfb
+    v0 = fields.kuo2004(n)
+    c0 = fields.gaussian(n)
+    team = xfb.LoopbackTeam(n, p, c)
+    team.set_vorticity(v0)
+    team.set_tracer(v0, 6.5)
+    team.step(3, 3.0)
+    assert np.array_equal(team.get_field(xfb.capi.TRACER), team.get_field(xfb.capi.VORT))
+    team.set_vorticity(v0)
+    team.set_tracer(c0, 20.0)
+    team.step(3, 3.0)
+    got = team.get_field(xfb.capi.TRACER)
+    team.close()
+    one = xfb.Backend(n)
+    one.set_vorticity(v0)
+    one.set_tracer(c0, 20.0)
+    one.step(3, 3.0)
+    ref = one.get_field(xfb.capi.TRACER)
+    one.close()
     assert rel_l2(got, ref) < 2e-6, rel_l2(got, ref)

@@ -194,3 +194,19 @@ def test_main_out_tracer_files():
             got = np.fromfile(os.path.join(d, "output", f"tracer_step_{s}.bin"), np.float32).reshape(n, n)
             assert rel_l2(got, o.get_tracer()) < 1e-5, s
             o.step(rec, 3.0)
+
+
+@pytest.mark.gpu
+def test_tracer_on_the_16384_grid():
+    """the two-level kernels of 16384-point lines carry the tracer too: a tracer equal to the vorticity with kappa = nu and
+    no forcing stays bit-identical to it"""
+    import xlab_fftbarotropic_b200 as xfb
+    n = 16384
+    x = (np.arange(n, dtype=np.float32) / n)
+    v0 = (5e-3 * np.exp(-((x[:, None] - 0.5) / 0.07) ** 2 - ((x[None, :] - 0.45) / 0.04) ** 2)).astype(np.float32)
+    b = xfb.Backend(n)
+    b.set_vorticity(v0)
+    b.set_tracer(v0, 6.5)
+    b.step(1, 0.25)
+    assert np.array_equal(b.get_field(xfb.capi.TRACER), b.get_field(xfb.capi.VORT))
+    b.close()

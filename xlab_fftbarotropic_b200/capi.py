@@ -26,7 +26,7 @@ SYMBOLS = [
     "xfb_slab_partition", "xfb_nccl_unique_id", "xfb_create_dist", "xfb_profile_read_a2a", "xfb_slab_transport", "xfb_slab_fused",
     "xfb_loopback_create", "xfb_loopback_destroy", "xfb_loopback_set_vorticity", "xfb_loopback_set_source",
     "xfb_loopback_step", "xfb_loopback_get_field", "xfb_loopback_launch_count", "xfb_loopback_get_diagnostics",
-    "xfb_loopback_get_keff_hist",
+    "xfb_loopback_get_keff_hist", "xfb_loopback_set_tracer",
 ]
 
 _lib = None
@@ -88,6 +88,7 @@ def load():
     L.xfb_loopback_set_source.argtypes = [vp, vp]
     L.xfb_loopback_step.argtypes = [vp, ci, cf]
     L.xfb_loopback_get_field.argtypes = [vp, ci, vp]
+    L.xfb_loopback_set_tracer.argtypes = [vp, vp, cf]
     L.xfb_loopback_get_diagnostics.argtypes = [vp, vp, vp]
     L.xfb_loopback_get_keff_hist.argtypes = [vp, ci, cf, cf, vp, vp]
     L.xfb_loopback_launch_count.restype = C.c_longlong
@@ -302,6 +303,11 @@ class SlabBackend(Backend):
         self._ck(self._L.xfb_get_field(self._h, 0, which, _ptr(out)))
         return out
 
+    def set_tracer(self, c, kappa, member=0):
+        if not isinstance(c, (int, np.integer)):
+            c = np.ascontiguousarray(c, dtype=np.float32).reshape(self.rows, self.ny)
+        self._ck(self._L.xfb_set_tracer(self._h, 0, _ptr(c), float(kappa)))
+
     def diagnostics(self, member=0):
         t = np.empty((self.rows, self.ny), np.float32)
         d = np.empty((self.rows, self.ny), np.float32)
@@ -364,6 +370,10 @@ class LoopbackTeam:
         else:
             s = np.ascontiguousarray(s, dtype=np.float32).reshape(self.n, self.n)
             self._ck(self._L.xfb_loopback_set_source(self._t, _ptr(s)))
+
+    def set_tracer(self, c, kappa):
+        c = np.ascontiguousarray(c, dtype=np.float32).reshape(self.n, self.n)
+        self._ck(self._L.xfb_loopback_set_tracer(self._t, _ptr(c), float(kappa)))
 
     def step(self, nsteps, dt):
         self._ck(self._L.xfb_loopback_step(self._t, int(nsteps), float(dt)))

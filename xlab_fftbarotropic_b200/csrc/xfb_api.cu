@@ -279,10 +279,14 @@ static int create_body(xfb_handle h, int size_class, int nx, int ny, float lx, f
     CK(cudaMemsetAsync(h->spec_a, 0, sizeof(cpx) * h->hpad, h->stream));
     CK(cudaMemsetAsync(h->spec_b, 0, sizeof(cpx) * h->hpad, h->stream));
     if (nranks > 1) {
-        if (dev_alloc((void **)&h->recv_block, 5 * sb)) return XFB_E_CUDA;
-        CK(cudaMemsetAsync(h->recv_block, 0, 5 * sb, h->stream));
+        // receive arrays of both transposes in ONE allocation (one CUDA-IPC mapping per peer): the tendency, the four
+        // products, and the same three arrays of the passive tracer (384 MB more per rank at 16384^2 on 8 GPUs)
+        if (dev_alloc((void **)&h->recv_block, 8 * sb)) return XFB_E_CUDA;
+        CK(cudaMemsetAsync(h->recv_block, 0, 8 * sb, h->stream));
         h->jint_recv = h->recv_block;
         for (int f = 0; f < 4; ++f) h->tr[f] = h->recv_block + (size_t)(1 + f) * h->hpad;
+        h->cjint_recv = h->recv_block + (size_t)5 * h->hpad;
+        for (int f = 0; f < 2; ++f) h->trc[f] = h->recv_block + (size_t)(6 + f) * h->hpad;
         if (dev_alloc((void **)&h->sync_buf, sizeof(float))) return XFB_E_CUDA;
         CK(cudaMemsetAsync(h->sync_buf, 0, sizeof(float), h->stream));
         {
@@ -328,7 +332,7 @@ int xfb::destroy_impl(xfb_handle h)
         cudaStreamDestroy(h->rec_stream);
     }
     void *ptrs[] = {h->tw, h->kx, h->ky, h->kx2, h->ky2, h->z0, h->zk, h->acc, h->jint, h->t_block, h->src, h->dg, h->real_a,
-                    h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b, h->recv_block, h->sync_buf, h->c0, h->ck, h->cacc, h->cjint, h->tc[0], h->panel_base};
+                    h->real_b, h->real_c, h->spec_a, h->spec_b, h->ref_a, h->ref_b, h->recv_block, h->sync_buf, h->c0, h->ck, h->cacc, h->cjint, h->tc[0], h->panel_base, h->panel_base_c};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (auto pool : {h->ev_row, h->ev_col, h->ev_a2a})
@@ -654,8 +658,9 @@ extern "C" int xfb_set_tracer(xfb_handle h, int member, const float *tracer, flo
 {
     if (check_member(h, member)) return XFB_E_ARG;
     if (!tracer) return fail(XFB_E_ARG, "null tracer");
-    if (!fused_diag_ok(h) && !h->generic)
-        return fail(XFB_E_SIZE, "the passive tracer needs a single-GPU grid <= 8192 (fused kernels) or a generic mixed-radix grid");
+    static const bool gen1_col = getenv("XFB_COL_GEN1") && atoi(getenv("XFB_COL_GEN1")) != 0;
+    if (!fused_diag_ok(h) && !h->generic && h->nranks == 1 && !(h->nx == 16384 && col_two_level(h->nx) && !gen1_col))
+        return fail(XFB_E_SIZE, "the passive tracer needs the fused kernels (power-of-two grids), a generic mixed-radix grid, or a slab-decomposed handle");
     CK(cudaSetDevice(h->device));
     const size_t sb = sizeof(cpx) * h->hpad * h->batch;
     if (!h->c0) {
@@ -672,11 +677,20 @@ extern "C" int xfb_set_tracer(xfb_handle h, int member, const float *tracer, flo
     }
     const void *din;
     if (stage_in(h, tracer, h->real_a, sizeof(float) * h->grids, &din)) return XFB_E_CUDA;
-    if (h->generic) {
+    if (h->nranks > 1) {
+        if (int e = dist_set_tracer(h, (const float *)din)) return e;          // local rows; collective
+    } else if (h->generic) {
         if (fwd2d(h, (const float *)din, h->spec_a, h->spec_b)) return XFB_E_CUDA;
         if (launch_pw(h, OP_COPY, h->spec_b, h->pitch, h->c0 + (size_t)member * h->hpad, h->pitch, h->pitch, 0, h->tw_state))
             return XFB_E_CUDA;
-    } else if (fused_forward_to_state(h, (const float *)din, h->c0 + (size_t)member * h->hpad)) return XFB_E_CUDA;
+    } else if (fused_diag_ok(h)) {
+        if (fused_forward_to_state(h, (const float *)din, h->c0 + (size_t)member * h->hpad)) return XFB_E_CUDA;
+    } else {
+        // 16384-point lines: plain transforms, then the layout conversion into the tile-major state
+        if (fwd2d(h, (const float *)din, h->spec_a, h->spec_b)) return XFB_E_CUDA;
+        if (launch_pw(h, OP_COPY, h->spec_b, h->pitch, h->c0 + (size_t)member * h->hpad, h->pitch, h->pitch, 0, h->tw_state))
+            return XFB_E_CUDA;
+    }
     if (!h->has_tracer || h->kappa != kappa) {
         // the captured step has no tracer launches / another diffusivity baked in
         if (h->step_graph) { cudaGraphExecDestroy((cudaGraphExec_t)h->step_graph); h->step_graph = nullptr; }
@@ -1119,6 +1133,11 @@ extern "C" int xfb_get_tracer_keff_hist(xfb_handle h, int member, int nbins, flo
 {
     if (check_member(h, member)) return XFB_E_ARG;
     if (!h->has_tracer) return fail(XFB_E_STATE, "xfb_get_tracer_keff_hist before xfb_set_tracer");
+    if (h->nranks > 1) {
+        if (!area || !grad2 || nbins < 1 || nbins > 2048 || !(cmax > cmin)) return fail(XFB_E_ARG, "bad histogram arguments");
+        CK(cudaSetDevice(h->device));
+        return dist_tracer_keff_hist(h, nbins, cmin, cmax, area, grad2);
+    }
     return keff_hist_impl(h, member, nbins, cmin, cmax, area, grad2, h->c0);
 }
 

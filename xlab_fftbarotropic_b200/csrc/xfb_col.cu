@@ -105,7 +105,7 @@ static int launch_col2l_t(const ColParams &p, int batch, cudaStream_t st)
     const int resident = cfg.get([&](int *e) { return resident_ctas(col2l_kernel<NX, MODE>, C::THREADS, C::SMEM, C::TCOLS, e); }, &err);
     if (resident <= 0) return err;
     CUtensorMap jmap = CUtensorMap();
-    if (MODE == COL_STEP)      // one-column boxes of the tendency: 2 elements (one 16-byte piece) x BOXR row pairs
+    if (MODE == COL_STEP || MODE == COL_TSTEP)      // one-column boxes of the tendency: 2 elements (one 16-byte piece) x BOXR row pairs
         if (int e = make_pair_map(&jmap, p.jint, (long long)NX * batch, p.pitch, 1, C::BOXR)) return e;
     const int ncols = p.pitch * batch;
     int blocks = ncols < resident ? ncols : resident;
@@ -181,6 +181,8 @@ int launch_col(int nx, int mode, const ColParams &p, int batch, cudaStream_t st)
             return mode == COL_STEP ? launch_col2l_t<16384, COL_STEP>(p, batch, st) : launch_col2l_t<16384, COL_PRO>(p, batch, st);
         return mode == COL_STEP ? launch_col2l_t<4096, COL_STEP>(p, batch, st) : launch_col2l_t<4096, COL_PRO>(p, batch, st);
     }
+    if ((mode == COL_TSTEP || mode == COL_TPRO) && nx == 16384 && col_two_level(nx))     // passive tracer on the 16384 grid
+        return mode == COL_TSTEP ? launch_col2l_t<16384, COL_TSTEP>(p, batch, st) : launch_col2l_t<16384, COL_TPRO>(p, batch, st);
     const bool colt_only = (mode == COL_DIAG || mode == COL_FWDT || mode == COL_TSTEP || mode == COL_TPRO);
     if (colt_only && (gen1 || nx > 8192)) return (int)cudaErrorNotSupported;
     if ((mode == COL_STEP || mode == COL_PRO || colt_only) && !gen1) {

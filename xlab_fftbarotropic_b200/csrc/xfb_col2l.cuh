@@ -94,11 +94,17 @@ struct Col2LRing {
     __device__ __forceinline__ void operator()(const int e, const bool) { if (e < 2) step(); }
 };
 
-template <int NX, int MODE>
+template <int NX, int MODE_>
 __global__ void __launch_bounds__(Col2LCfg<NX>::THREADS, 1)
 col2l_kernel(const ColParams p, const __grid_constant__ CUtensorMap jmap, const int ncols)
 {
     typedef Col2LCfg<NX> C;
+    // the tracer modes are the stepper's modes with two products (i kx C, i ky C) instead of four
+    constexpr bool TRACER = (MODE_ == COL_TSTEP || MODE_ == COL_TPRO);
+    constexpr int MODE = (MODE_ == COL_TSTEP) ? COL_STEP : (MODE_ == COL_TPRO) ? COL_PRO : MODE_;
+    // the ring needs the 16 hook points of EIGHT inverse transforms per column; the tracer step has four: its columns all
+    // come with the burst of 16-byte loads (a half-streamed column would leave loads in flight behind the next begin())
+    constexpr bool RING = !TRACER;
     constexpr int H = C::H, G = C::G;
     // TMA needs 128-byte aligned shared addresses: the declared alignment makes every offset below a link-time constant
     // (an alignment computed at run time costs registers that the transforms then spill)
@@ -159,7 +165,7 @@ col2l_kernel(const ColParams p, const __grid_constant__ CUtensorMap jmap, const 
 
         if (MODE == COL_STEP) {
             // ------------------------------------------------------------ forward (decimation in time) + epilogue
-            if (col == (int)blockIdx.x) {
+            if (!RING || col == (int)blockIdx.x) {
                 // the CTA's first column has nothing to hide a stream behind (a slab chunk may hold a single column per
                 // CTA, and a one-column TMA box moves 16-byte rows at a crawl): its sixteen pieces come with one burst of
                 // 16-byte loads and take the same way through tensor memory as the streamed columns
@@ -196,7 +202,7 @@ col2l_kernel(const ColParams p, const __grid_constant__ CUtensorMap jmap, const 
             {
                 // the incoming region is free: the next column of this CTA streams into it under the inverse transforms
                 const int nc = col + gridDim.x;
-                if (nc < ncols) {
+                if (RING && nc < ncols) {
                     const int nm = nc / p.pitch, njl = nc - nm * p.pitch;
                     rs.begin(njl * 2, nm * (NX / 2));
                 } else {
@@ -293,7 +299,7 @@ col2l_kernel(const ColParams p, const __grid_constant__ CUtensorMap jmap, const 
         // ---------------------------------------------------------------- prologue of the next stage + 4 inverse
         // (decimation in frequency; inverse transforms by the swap trick: every value enters and leaves swapped)
 #pragma unroll 1
-        for (int f = 0; f < 4; ++f) {
+        for (int f = 0; f < (TRACER ? 2 : 4); ++f) {
             const cpx wl = launder(wt);
             // the thread index is laundered per field: otherwise the sixteen 64-bit store addresses are hoisted out of
             // this loop and spilled

@@ -110,6 +110,11 @@ static int build_panel_table(xfb_handle h, cpx *const *recv_of_rank)
         for (int c = 0; c < h->nchunks; ++c) tab[q * h->nchunks + c] = recv_of_rank[q] + col_off(h, h->rank, c, 0);
     if (dev_alloc((void **)&h->panel_base, sizeof(cpx *) * n)) return XFB_E_CUDA;
     CK(cudaMemcpy(h->panel_base, tab.data(), sizeof(cpx *) * n, cudaMemcpyHostToDevice));
+    // the tracer's tendency lands in array 5 of the receive blocks (cjint_recv)
+    for (int q = 0; q < h->nranks; ++q)
+        for (int c = 0; c < h->nchunks; ++c) tab[q * h->nchunks + c] = recv_of_rank[q] + (size_t)5 * h->hpad + col_off(h, h->rank, c, 0);
+    if (dev_alloc((void **)&h->panel_base_c, sizeof(cpx *) * n)) return XFB_E_CUDA;
+    CK(cudaMemcpy(h->panel_base_c, tab.data(), sizeof(cpx *) * n, cudaMemcpyHostToDevice));
     // Fused column -> row exchange, OPT-IN (XFB_SLAB_FUSED_COL=1): K-COL stores each product row straight into the
     // receive array tr[f] of the rank that owns the row (array 1 + f of that rank's receive block), at the block of
     // panels (me, 0 .. nchunks-1).  Served by the first-generation column kernel (the line lengths > 8192 run on it).
@@ -158,8 +163,11 @@ __global__ void __launch_bounds__(512) push_kernel(const PushSegs s)
 // One all-to-all of the blocks (column chunks [c0, c1), local rows [r0, r1)) of `na` arrays.
 // NCCL: issued for the single local rank on `st`.  Loopback: device copies for every rank on the shared stream.
 static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *col_ptrs_of_rank, int na, int c0, int c1, int r0,
-                    int r1, cudaStream_t st, bool skip_self = false)
+                    int r1, cudaStream_t st, bool skip_self = false, int abase = -1)
 {
+    // abase: index of the first destination array inside the peers' receive blocks (P2P transports): the vorticity uses
+    // 0 (jint_recv) for ROW2COL and 1.. (tr[0..3]) for COL2ROW, the tracer 5 (cjint_recv) and 6.. (trc[0..1])
+    if (abase < 0) abase = (dir == ROW2COL) ? 0 : 1;
     // skip_self: the producer has already put every rank's own block in place (two-level K-COL, ColParams::self_out)
     // row_ptrs_of_rank / col_ptrs_of_rank: [nlocal][na]
     xfb_handle h0 = T->local[0];
@@ -211,10 +219,11 @@ static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *
                 const int q = (me + i) % T->nranks;
                 cpx *peer = h0->peer_recv[q];
                 for (int c = c0; c < c1; ++c) {
-                    if (dir == ROW2COL) add(peer + col_off(h0, me, c, r0), row_ptrs_of_rank[0] + row_off(h0, q, c, r0), count);
+                    if (dir == ROW2COL)
+                        add(peer + (size_t)abase * h0->hpad + col_off(h0, me, c, r0), row_ptrs_of_rank[0] + row_off(h0, q, c, r0), count);
                     else
                         for (int a = 0; a < na; ++a)
-                            add(peer + (size_t)(1 + a) * h0->hpad + row_off(h0, me, c, r0), col_ptrs_of_rank[a] + col_off(h0, q, c, r0), count);
+                            add(peer + (size_t)(abase + a) * h0->hpad + row_off(h0, me, c, r0), col_ptrs_of_rank[a] + col_off(h0, q, c, r0), count);
                     if (segs.n + 4 > 64)
                         if (int e = flush()) return e;
                 }
@@ -239,7 +248,7 @@ static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *
                 if (dir == ROW2COL) {
                     // array 0 of the receive block = jint_recv ; chunks c0..c1-1 are rows*cw apart here, NX*cw apart there
                     const cpx *src = row_ptrs_of_rank[0] + row_off(h0, q, c0, r0) + e0;
-                    cpx *dst = peer + col_off(h0, me, c0, r0) + e0;
+                    cpx *dst = peer + (size_t)abase * h0->hpad + col_off(h0, me, c0, r0) + e0;
                     if (one_d) {
                         for (int c = c0; c < c1; ++c)
                             CK(cudaMemcpyAsync(dst + (size_t)(c - c0) * h0->nx * h0->pitch, src + (size_t)(c - c0) * h0->rows * h0->pitch,
@@ -252,16 +261,16 @@ static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *
                     for (int c = c0; c < c1; ++c) {
                         if (na == 4 && one_d) {
                             for (int a = 0; a < 4; ++a)
-                                CK(cudaMemcpyAsync(peer + (size_t)(1 + a) * h0->hpad + row_off(h0, me, c, r0) + e0,
+                                CK(cudaMemcpyAsync(peer + (size_t)(abase + a) * h0->hpad + row_off(h0, me, c, r0) + e0,
                                                    col_ptrs_of_rank[a] + col_off(h0, q, c, r0) + e0, wbytes, cudaMemcpyDeviceToDevice, cs));
                         } else if (na == 4) {
                             const cpx *src = col_ptrs_of_rank[0] + col_off(h0, q, c, r0) + e0;     // t[0]; t[1..3] follow hpad apart
-                            cpx *dst = peer + h0->hpad + row_off(h0, me, c, r0) + e0;
+                            cpx *dst = peer + (size_t)abase * h0->hpad + row_off(h0, me, c, r0) + e0;
                             CK(cudaMemcpy2DAsync(dst, sizeof(cpx) * h0->hpad, src, sizeof(cpx) * h0->hpad, wbytes, 4,
                                                  cudaMemcpyDeviceToDevice, cs));
                         } else {
                             for (int a = 0; a < na; ++a)
-                                CK(cudaMemcpyAsync(peer + (size_t)(1 + a) * h0->hpad + row_off(h0, me, c, r0) + e0,
+                                CK(cudaMemcpyAsync(peer + (size_t)(abase + a) * h0->hpad + row_off(h0, me, c, r0) + e0,
                                                    col_ptrs_of_rank[a] + col_off(h0, q, c, r0) + e0, wbytes, cudaMemcpyDeviceToDevice, cs));
                         }
                     }
@@ -297,12 +306,12 @@ static int exchange(Team *T, int dir, cpx *const *row_ptrs_of_rank, cpx *const *
 
 // ---- per-rank launches --------------------------------------------------------------------------------
 static int launch_row_chunk(xfb_handle h, int mode, const cpx *const in[4], const float *real_in, cpx *spec_out, float *real_out,
-                            int negate, int r0, int r1, bool fused_out = false)
+                            int negate, int r0, int r1, bool fused_out = false, bool tracer = false)
 {
     RowParams r;
     fill_row(h, r, r1 - r0);
     const size_t so = (size_t)r0 * h->pitch, ro = (size_t)r0 * h->ny;
-    if (fused_out && h->panel_base) { r.panel_base = h->panel_base; r.out_row_off = (long long)so; }
+    if (fused_out && h->panel_base) { r.panel_base = tracer ? h->panel_base_c : h->panel_base; r.out_row_off = (long long)so; }
     for (int f = 0; f < 4; ++f) r.spec_in[f] = in && in[f] ? in[f] + so : nullptr;
     r.real_in = real_in ? real_in + ro : nullptr;
     r.spec_out = spec_out ? spec_out + so : nullptr;
@@ -312,7 +321,9 @@ static int launch_row_chunk(xfb_handle h, int mode, const cpx *const in[4], cons
     return 0;
 }
 
-static int launch_col_chunk(xfb_handle h, int mode, int chunk, int stage, float dt, const cpx *inv_in, cpx *inv_out)
+// tracer: the same launch on the passive tracer's arrays (state c0 / ck / cacc, tendency cjint_recv, two gradient
+// products tc[0..1], diffusivity kappa); `mode` is then COL_TSTEP / COL_TPRO (or COL_FWD into c0)
+static int launch_col_chunk(xfb_handle h, int mode, int chunk, int stage, float dt, const cpx *inv_in, cpx *inv_out, bool tracer = false)
 {
     ColParams c;
     fill_col(h, c, chunk);
@@ -320,15 +331,20 @@ static int launch_col_chunk(xfb_handle h, int mode, int chunk, int stage, float 
     c.jint = h->jint_recv + off; c.z0 = h->z0 + off; c.zk = h->zk + off; c.acc = h->acc + off;
     c.st_tile_stride = (long long)h->nx * h->tw_state; c.st_row_stride = h->tw_state;     // tile-major state
     for (int f = 0; f < 4; ++f) c.t_out[f] = h->t[f] + off;
+    if (tracer) {
+        c.z0 = h->c0 + off; c.zk = h->ck + off; c.acc = h->cacc + off; c.nu = h->kappa;
+        if (mode != COL_FWD) c.jint = h->cjint_recv + off;       // COL_FWD: the field just travelled through jint_recv
+        for (int f = 0; f < 4; ++f) c.t_out[f] = h->tc[f & 1] + off;
+    }
     if (mode == COL_INV) { c.inv_in = inv_in + off; c.t_out[0] = inv_out + off; }
     c.dt = dt; c.stage = stage;
     c.dt_stage = (stage == 3) ? dt : dt / 2.0f;          // main.cpp:296,299,302
-    if (h->self_direct && (mode == COL_STEP || mode == COL_PRO)) {
+    if (h->self_direct && (mode == COL_STEP || mode == COL_PRO || mode == COL_TSTEP || mode == COL_TPRO)) {
         c.self_piece0 = h->rank * (h->rows / 2);
         c.self_pieces = h->rows / 2;
-        for (int f = 0; f < 4; ++f) c.self_out[f] = h->tr[f] + row_off(h, h->rank, chunk, 0);
+        for (int f = 0; f < 4; ++f) c.self_out[f] = (tracer ? h->trc[f & 1] : h->tr[f]) + row_off(h, h->rank, chunk, 0);
     }
-    if (h->fused_col && mode != COL_FWD) {
+    if (h->fused_col && mode != COL_FWD && !tracer) {
         c.peer_rows = h->rows;
         c.peer_rows_shift = 0;
         while ((1 << c.peer_rows_shift) < h->rows) ++c.peer_rows_shift;
@@ -378,7 +394,7 @@ static void a2a_mark(xfb_handle h, cudaStream_t st)
 // y pass for all local ranks (row chunks) + exchange into the column side.
 //   produce(h, r0, r1) launches K-ROW on local rows [r0, r1) ; row_of(h) / col_of(h) name the two arrays
 template <typename F, typename GR, typename GC>
-static int rows_then_exchange(Team *T, F produce, GR row_of, GC col_of)
+static int rows_then_exchange(Team *T, F produce, GR row_of, GC col_of, int abase = 0)
 {
     xfb_handle h0 = T->local[0];
     const int C = h0->nchunks, rc = h0->rows / C;
@@ -400,14 +416,14 @@ static int rows_then_exchange(Team *T, F produce, GR row_of, GC col_of)
         for (int l = 0; l < T->nlocal; ++l)
             for (int i = 0; i < C; ++i)
                 if (int e = produce(T->local[l], i * rc, (i + 1) * rc)) return e;
-        return exchange(T, ROW2COL, rp, cp, 1, 0, C, 0, h0->rows, h0->stream);
+        return exchange(T, ROW2COL, rp, cp, 1, 0, C, 0, h0->rows, h0->stream, false, abase);
     }
     for (int i = 0; i < C; ++i) {
         if (int e = produce(h0, i * rc, (i + 1) * rc)) return e;
         CK(cudaEventRecord(h0->ev_chunk[i], h0->stream));
         CK(cudaStreamWaitEvent(h0->comm_stream, h0->ev_chunk[i], 0));
         a2a_mark(h0, h0->comm_stream);
-        if (int e = exchange(T, ROW2COL, rp, cp, 1, 0, C, i * rc, (i + 1) * rc, h0->comm_stream)) return e;
+        if (int e = exchange(T, ROW2COL, rp, cp, 1, 0, C, i * rc, (i + 1) * rc, h0->comm_stream, false, abase)) return e;
         a2a_mark(h0, h0->comm_stream);
     }
     if (int e = phase_barrier(T, h0->comm_stream)) return e;
@@ -419,14 +435,14 @@ static int rows_then_exchange(Team *T, F produce, GR row_of, GC col_of)
 // x pass for all local ranks (column chunks) + exchange of `na` arrays back to the row side.
 //   produce(h, chunk) launches K-COL ; col_of(h, a) / row_of(h, a) name array a on the two sides
 template <typename F, typename GC, typename GR>
-static int cols_then_exchange(Team *T, F produce, GC col_of, GR row_of, int na, bool skip_self = false)
+static int cols_then_exchange(Team *T, F produce, GC col_of, GR row_of, int na, bool skip_self = false, int abase = 1)
 {
     xfb_handle h0 = T->local[0];
     const int C = h0->nchunks;
     cpx *rp[16 * 4], *cp[16 * 4];
     for (int l = 0; l < T->nlocal; ++l)
         for (int a = 0; a < na; ++a) { rp[l * na + a] = row_of(T->local[l], a); cp[l * na + a] = col_of(T->local[l], a); }
-    if (h0->fused_col) {
+    if (h0->fused_col && abase == 1) {
         // fused exchange: the kernels have stored into the owners' receive arrays themselves; what is left is the barrier
         for (int l = 0; l < T->nlocal; ++l)
             for (int c = 0; c < C; ++c)
@@ -443,14 +459,14 @@ static int cols_then_exchange(Team *T, F produce, GC col_of, GR row_of, int na, 
         for (int l = 0; l < T->nlocal; ++l)
             for (int c = 0; c < C; ++c)
                 if (int e = produce(T->local[l], c)) return e;
-        return exchange(T, COL2ROW, rp, cp, na, 0, C, 0, h0->rows, h0->stream, skip_self);
+        return exchange(T, COL2ROW, rp, cp, na, 0, C, 0, h0->rows, h0->stream, skip_self, abase);
     }
     for (int c = 0; c < C; ++c) {
         if (int e = produce(h0, c)) return e;
         CK(cudaEventRecord(h0->ev_chunk[c], h0->stream));
         CK(cudaStreamWaitEvent(h0->comm_stream, h0->ev_chunk[c], 0));
         a2a_mark(h0, h0->comm_stream);
-        if (int e = exchange(T, COL2ROW, rp, cp, na, c, c + 1, 0, h0->rows, h0->comm_stream, skip_self)) return e;
+        if (int e = exchange(T, COL2ROW, rp, cp, na, c, c + 1, 0, h0->rows, h0->comm_stream, skip_self, abase)) return e;
         a2a_mark(h0, h0->comm_stream);
     }
     if (int e = phase_barrier(T, h0->comm_stream)) return e;
@@ -460,8 +476,8 @@ static int cols_then_exchange(Team *T, F produce, GC col_of, GR row_of, int na, 
 }
 
 // ---- team-level operations ------------------------------------------------------------------------------
-// vort[l]: device pointer to the local rows of rank local[l]
-static int team_set_vorticity(Team *T, const float *const *vort)
+// vort[l]: device pointer to the local rows of rank local[l]; tracer: the field becomes the passive tracer's state c0
+static int team_set_vorticity(Team *T, const float *const *vort, bool tracer = false)
 {
     int e = rows_then_exchange(
         T,
@@ -475,9 +491,13 @@ static int team_set_vorticity(Team *T, const float *const *vort)
     for (int l = 0; l < T->nlocal; ++l) {
         xfb_handle h = T->local[l];
         for (int c = 0; c < h->nchunks; ++c)
-            if (int e2 = launch_col_chunk(h, COL_FWD, c, 0, 0.f, nullptr, nullptr)) return e2;
-        h->have_state = true;
-        h->tf_valid = false;
+            if (int e2 = launch_col_chunk(h, COL_FWD, c, 0, 0.f, nullptr, nullptr, tracer)) return e2;
+        if (tracer) {
+            h->tcf_valid = false;
+        } else {
+            h->have_state = true;
+            h->tf_valid = false;
+        }
     }
     return team_fence(T);       // jint_recv has been consumed everywhere before anybody's next K-ROW stores into it
 }
@@ -489,12 +509,25 @@ static int team_products(Team *T, int mode, int stage, float dt)
         [](xfb_handle h, int a) { return h->t[a]; }, [](xfb_handle h, int a) { return h->tr[a]; }, 4, T->local[0]->self_direct);
 }
 
+// the tracer's two gradient products (i kx C, i ky C), x-inverse-transformed and sent to the row side (trc[0..1])
+static int team_tracer_products(Team *T, int mode, int stage, float dt)
+{
+    return cols_then_exchange(
+        T, [&](xfb_handle h, int c) { return launch_col_chunk(h, mode, c, stage, dt, nullptr, nullptr, true); },
+        [](xfb_handle h, int a) { return h->tc[a]; }, [](xfb_handle h, int a) { return h->trc[a]; }, 2, T->local[0]->self_direct, 6);
+}
+
 static int team_step(Team *T, int nsteps, float dt)
 {
     xfb_handle h0 = T->local[0];
+    const bool tracer = h0->has_tracer;
     if (nsteps > 0 && !h0->tf_valid) {
         if (int e = team_products(T, COL_PRO, 0, dt)) return e;
         for (int l = 0; l < T->nlocal; ++l) T->local[l]->tf_valid = true;
+    }
+    if (nsteps > 0 && tracer && !h0->tcf_valid) {
+        if (int e = team_tracer_products(T, COL_TPRO, 0, dt)) return e;
+        for (int l = 0; l < T->nlocal; ++l) T->local[l]->tcf_valid = true;
     }
     for (int s = 0; s < nsteps; ++s)
         for (int k = 1; k <= 4; ++k) {
@@ -506,11 +539,25 @@ static int team_step(Team *T, int nsteps, float dt)
                 },
                 [](xfb_handle h) { return h->jint; }, [](xfb_handle h) { return h->jint_recv; });
             if (e) return e;
+            if (tracer) {
+                // the tracer's Jacobian with the velocity of this stage: (T_cx, T_cy) from trc[], (T_u, T_v) from tr[2..3]
+                // -- before K-COL's exchange overwrites them (xfb_api.cu: xfb_step does the same on one GPU)
+                e = rows_then_exchange(
+                    T,
+                    [&](xfb_handle h, int r0, int r1) {
+                        const cpx *in[4] = {h->trc[0], h->trc[1], h->tr[2], h->tr[3]};
+                        return launch_row_chunk(h, ROW_JAC, in, nullptr, h->cjint, nullptr, 0, r0, r1, true, true);
+                    },
+                    [](xfb_handle h) { return h->cjint; }, [](xfb_handle h) { return h->cjint_recv; }, 5);
+                if (e) return e;
+            }
             if (h0->profiling && !T->loopback) {
                 cudaEventRecord(next_event(h0->ev_row, h0->ev_row_used), h0->stream);
                 cudaEventRecord(next_event(h0->ev_col, h0->ev_col_used), h0->stream);
             }
             if (int e2 = team_products(T, COL_STEP, k, dt)) return e2;
+            if (tracer)
+                if (int e3 = team_tracer_products(T, COL_TSTEP, k, dt)) return e3;
             if (h0->profiling && !T->loopback) cudaEventRecord(next_event(h0->ev_col, h0->ev_col_used), h0->stream);
         }
     return 0;
@@ -528,14 +575,14 @@ __global__ void dist_diag_kernel(const float *pxy, const float *pxx, const float
 }
 
 // spectral operator chain `ops` applied to the state, inverse 2-D transform, into dout[l] (device, local rows)
-static int team_inverse(Team *T, const int *ops, int nops, int negate, float *const *dout)
+static int team_inverse(Team *T, const int *ops, int nops, int negate, float *const *dout, bool tracer_state = false)
 {
     int e = cols_then_exchange(
         T,
         [&](xfb_handle h, int c) {
             const size_t off = (size_t)c * h->nx * h->pitch;
             const int P = h->pitch;
-            if (launch_pw(h, ops[0], h->z0 + off, P, h->spec_a + off, P, P, h->tw_state, 0, c)) return (int)XFB_E_CUDA;
+            if (launch_pw(h, ops[0], (tracer_state ? h->c0 : h->z0) + off, P, h->spec_a + off, P, P, h->tw_state, 0, c)) return (int)XFB_E_CUDA;
             for (int o = 1; o < nops; ++o)
                 if (launch_pw(h, ops[o], h->spec_a + off, P, h->spec_a + off, P, P, 0, 0, c)) return (int)XFB_E_CUDA;
             return launch_col_chunk(h, COL_INV, c, 0, 0.f, h->spec_a, h->spec_b);
@@ -558,6 +605,9 @@ static int team_get_field(Team *T, int which, float *const *dout)
                      op_pxx[] = {OP_INVLAP, OP_GRADX, OP_GRADX}, op_pyy[] = {OP_INVLAP, OP_GRADY, OP_GRADY};
     switch (which) {
     case XFB_VORT: return team_inverse(T, op_vort, 1, 0, dout);
+    case XFB_TRACER:
+        if (!T->local[0]->has_tracer) return fail(XFB_E_STATE, "XFB_TRACER before xfb_set_tracer");
+        return team_inverse(T, op_vort, 1, 0, dout, true);
     case XFB_PSI: return team_inverse(T, op_psi, 1, 0, dout);
     case XFB_U: return team_inverse(T, op_u, 2, 1, dout);
     case XFB_V: return team_inverse(T, op_v, 2, 0, dout);
@@ -609,14 +659,14 @@ static int team_diagnostics(Team *T, float *const *tfil, float *const *deform)
 
 // effective-diffusivity histograms: zeta, zeta_x, zeta_y of the local rows, binned per rank into `d[l]` (2 * nbins doubles,
 // device); the caller reduces over the ranks
-static int team_keff_hist(Team *T, int nbins, float cmin, float cmax, double *const *d)
+static int team_keff_hist(Team *T, int nbins, float cmin, float cmax, double *const *d, bool tracer_state = false)
 {
     static const int op_vort[] = {OP_COPY}, op_zx[] = {OP_GRADX}, op_zy[] = {OP_GRADY};
     float *a[16], *b[16], *c[16];
     for (int l = 0; l < T->nlocal; ++l) { a[l] = T->local[l]->real_a; b[l] = T->local[l]->real_b; c[l] = T->local[l]->real_c; }
-    if (int e = team_inverse(T, op_vort, 1, 0, a)) return e;
-    if (int e = team_inverse(T, op_zx, 1, 0, b)) return e;
-    if (int e = team_inverse(T, op_zy, 1, 0, c)) return e;
+    if (int e = team_inverse(T, op_vort, 1, 0, a, tracer_state)) return e;
+    if (int e = team_inverse(T, op_zx, 1, 0, b, tracer_state)) return e;
+    if (int e = team_inverse(T, op_zy, 1, 0, c, tracer_state)) return e;
     // the inverses above use the spectral scratch arrays the caller may have taken `d` from: zero it only now
     CK(cudaMemsetAsync(d[0], 0, sizeof(double) * 2 * nbins, T->local[0]->stream));
     for (int l = 1; l < T->nlocal; ++l)
@@ -629,11 +679,20 @@ static int team_keff_hist(Team *T, int nbins, float cmin, float cmax, double *co
 }
 
 // ---- entry points used by xfb_api.cu for NCCL handles ----------------------------------------------------
+static int dist_keff_hist_impl(xfb_handle h, int nbins, float cmin, float cmax, double *area, double *grad2, bool tracer_state);
 int dist_keff_hist(xfb_handle h, int nbins, float cmin, float cmax, double *area, double *grad2)
+{
+    return dist_keff_hist_impl(h, nbins, cmin, cmax, area, grad2, false);
+}
+int dist_tracer_keff_hist(xfb_handle h, int nbins, float cmin, float cmax, double *area, double *grad2)
+{
+    return dist_keff_hist_impl(h, nbins, cmin, cmax, area, grad2, true);
+}
+static int dist_keff_hist_impl(xfb_handle h, int nbins, float cmin, float cmax, double *area, double *grad2, bool tracer_state)
 {
     if (h->team->loopback) return fail(XFB_E_STATE, "loopback ranks are driven through xfb_loopback_*");
     double *d = (double *)h->spec_a;                 // free scratch of >= 2 * 2048 doubles once the inverses are done
-    if (int e = team_keff_hist(h->team, nbins, cmin, cmax, &d)) return e;
+    if (int e = team_keff_hist(h->team, nbins, cmin, cmax, &d, tracer_state)) return e;
     // one all-reduce of the 2 * nbins partial sums over the ranks
     NCK(g_nccl.AllReduce(d, d, (size_t)2 * nbins, ncclDouble, ncclSum, h->team->comm, h->stream));
     std::vector<double> host(2 * (size_t)nbins);
@@ -669,6 +728,13 @@ int dist_set_vorticity(xfb_handle h, const float *vort_rows)
     if (int e = team_set_vorticity(h->team, &din)) return e;
     if (!is_device_ptr(vort_rows)) CK(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+// the passive tracer's initial field (device pointer, local rows): y pass, exchange, x pass into c0; collective
+int dist_set_tracer(xfb_handle h, const float *tracer_rows_dev)
+{
+    if (h->team->loopback) return fail(XFB_E_STATE, "loopback ranks are driven through xfb_loopback_*");
+    return team_set_vorticity(h->team, &tracer_rows_dev, true);
 }
 
 int dist_step(xfb_handle h, int nsteps, float dt)
@@ -922,6 +988,35 @@ extern "C" int xfb_loopback_set_source(xfb_loopback_s *L, const float *src_full_
         xfb_handle h = L->team.local[r];
         if (int e = xfb_set_source(h, 0, src_full_host ? src_full_host + (size_t)r * h->rows * L->ny : nullptr)) return e;
     }
+    return 0;
+}
+
+extern "C" int xfb_loopback_set_tracer(xfb_loopback_s *L, const float *tracer_full_host, float kappa)
+{
+    if (!L || !tracer_full_host) return fail(XFB_E_ARG, "null argument");
+    xfb_handle h0 = L->team.local[0];
+    CK(cudaSetDevice(h0->device));
+    for (int r = 0; r < L->team.nranks; ++r) {
+        xfb_handle h = L->team.local[r];
+        const size_t sb = sizeof(cpx) * h->hpad;
+        if (!h->c0) {
+            cpx **state[] = {&h->c0, &h->ck, &h->cacc, &h->cjint};
+            for (auto pp : state) {
+                if (dev_alloc((void **)pp, sb)) return XFB_E_CUDA;
+                CK(cudaMemsetAsync(*pp, 0, sb, h->stream));
+            }
+            if (dev_alloc((void **)&h->tc[0], 2 * sb)) return XFB_E_CUDA;
+            CK(cudaMemsetAsync(h->tc[0], 0, 2 * sb, h->stream));
+            h->tc[1] = h->tc[0] + h->hpad;
+        }
+        h->has_tracer = true;
+        h->kappa = kappa;
+    }
+    CK(cudaMemcpyAsync(L->full, tracer_full_host, sizeof(float) * (size_t)L->nx * L->ny, cudaMemcpyHostToDevice, h0->stream));
+    const float *rows[16];
+    for (int r = 0; r < L->team.nranks; ++r) rows[r] = L->full + (size_t)r * h0->rows * L->ny;
+    if (int e = team_set_vorticity(&L->team, rows, true)) return e;
+    CK(cudaStreamSynchronize(h0->stream));
     return 0;
 }
 

@@ -77,7 +77,8 @@ struct xfb_handle_s {
     unsigned cw_magic;
     xfb::Team *team;
     xfb::cpx *jint_recv, *tr[4];    // receive sides of the two transposes: ONE allocation (recv_block), exported over CUDA IPC
-    xfb::cpx *t_block, *recv_block; // t[0..3] back to back ; jint_recv, tr[0..3] back to back
+    xfb::cpx *cjint_recv, *trc[2];  // the same for the passive tracer (arrays 5, 6, 7 of recv_block)
+    xfb::cpx *t_block, *recv_block; // t[0..3] back to back ; jint_recv, tr[0..3], cjint_recv, trc[0..1] back to back
     xfb::cpx *peer_recv[16];        // recv_block of every rank mapped into this process (peer-to-peer over NVLink)
     float *sync_buf;                // 1 float, reduced over all ranks as the phase barrier
     bool p2p;                       // exchange by pushes into peer_recv (else ncclSend/ncclRecv)
@@ -88,6 +89,7 @@ struct xfb_handle_s {
     bool self_direct;               // two-level K-COL stores this rank's own row pairs straight into its tr[] arrays (no self-copy in the push)
     bool fused_col;                 // fused column->row exchange: K-COL stores its product rows straight into the owners' receive arrays
     xfb::cpx *peer_tr[16][4];       // [rank][f]: block of rank's receive array tr[f] that holds THIS rank's column chunks
+    xfb::cpx **panel_base_c;        // the same table for the tracer's tendency (array 5 of the receive blocks)
     cudaStream_t comm_stream;
     cudaStream_t copy_stream[4];    // p2p transport: the pushes of one exchange are spread over several copy engines
     cudaEvent_t ev_copy[4], ev_fork;
@@ -135,6 +137,8 @@ int launch_keff_hist(xfb_handle h, const float *c, const float *gx, const float 
 int dist_keff_hist(xfb_handle h, int nbins, float cmin, float cmax, double *area, double *grad2);
 int dist_diagnostics(xfb_handle h, float *tfil_rows, float *deform_rows);
 int dist_set_vorticity(xfb_handle h, const float *vort_rows);
+int dist_set_tracer(xfb_handle h, const float *tracer_rows);
+int dist_tracer_keff_hist(xfb_handle h, int nbins, float cmin, float cmax, double *area, double *grad2);
 int dist_step(xfb_handle h, int nsteps, float dt);
 int dist_get_field(xfb_handle h, int which, float *out_rows);
 void dist_release(xfb_handle h);
