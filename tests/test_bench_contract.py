@@ -16,8 +16,9 @@ def _run(args, timeout):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=timeout,
                        cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
-    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-    assert len(lines) == 1, r.stdout
+    # ONE line on stdout, and it is the JSON line (libraries that print to fd 1 -- NCCL's version banner -- go to stderr)
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1 and lines[0].startswith("{"), r.stdout
     return json.loads(lines[0])
 
 
@@ -30,6 +31,17 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_reference_arm_line_for_the_slab_configuration():
+    """N > 1: the product arm is the slab-decomposed constant vortex (strong scaling); the reference arm must name the
+    same workload and scaling (rank 0 runs it; here with a tiny grid instead of 16384^2)"""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "main_n256.out")):
+        pytest.skip("oracle/_ref not built (needs /root/reference or the prebuilt binaries)")
+    d = _run(["--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1", "--ref-grid", "256"], 300)
+    assert d["impl"] == "reference" and d["scaling"] == "strong" and d["n_gpus"] == 2
+    assert "const vortex 16384^2" in d["config"]["workload"] and d["config"]["same_grid_as_product_arm"] is False
+    assert d["cpu_baseline"]["single_thread"]["cores"] == 1
 
 
 @pytest.mark.gpu
