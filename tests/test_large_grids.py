@@ -106,6 +106,8 @@ import fields, xlab_fftbarotropic_b200 as xfb
 n = {n}
 b = xfb.Backend(n)
 b.set_vorticity(fields.elliptic(n))
+x = np.arange(n, dtype=np.float32) / n
+b.set_source((2e-8 * np.sin(2 * np.pi * 3 * x)[:, None] * np.cos(2 * np.pi * 5 * x)[None, :]).astype(np.float32))   # the forcing path too
 b.step(2, {dt})
 np.save({out!r}, b.get_spectrum())
 """
