@@ -498,7 +498,7 @@ def main():
     ap.add_argument("--grid", type=int, default=None, help="default 8192 at N = 1, 16384 (slab-decomposed) at N > 1")
     ap.add_argument("--members", type=int, default=1, help="ensemble members per GPU")
     ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--e2e-inflight", type=int, default=3, help="independent requests in flight in the end-to-end measurement")
+    ap.add_argument("--e2e-inflight", type=int, default=4, help="independent requests in flight in the end-to-end measurement")
     ap.add_argument("--ref-grid", type=int, default=0, help="grid of the CPU arm (default: the product arm's grid; the "
                                                             "cpu_baseline leg inside the N = 1 product run uses --cpu-grid)")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds the timed run may take")

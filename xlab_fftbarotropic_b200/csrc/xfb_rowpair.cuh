@@ -198,7 +198,9 @@ __device__ __forceinline__ void jac_pair_direct(const RowParams &p, unsigned cha
 // 2 * NY * 8 bytes per pair out of shared memory (131 KB at NY = 8192) and a sixth of the traffic off the shared-memory
 // pipe, and the freed space holds TWO staging buffers: the bulk fetch of field n+2 is issued as soon as field n has
 // been read, a whole transform ahead, so no fetch latency is exposed any more.
-// STATUS: correct (tests pass with XFB_ROW_TMEM=1), measured slower than the shared-memory parks -- see xfb_row.cu.
+// Default at NY >= 4096 (8192^2: 0.50 ms per launch against 0.58 with the shared-memory parks); below that several CTAs
+// per SM already overlap fetch and transform and the shared-memory parks of rowpair_kernel stay faster -- see
+// use_tmem_parks() in xfb_row.cu.
 template <int NY>
 struct PairTCfg {
     static constexpr int G = NY / 16;
