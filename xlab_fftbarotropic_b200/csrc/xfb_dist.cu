@@ -803,7 +803,11 @@ extern "C" int xfb_create_dist(xfb_handle *out, int nx, int ny, float lx, float 
         return fail(XFB_E_SIZE, "xfb_create_dist: %d local rows do not split into %d even chunks", h->rows, nchunks);
     }
     Team *T = new (std::nothrow) Team();
-    if (!T) return fail(XFB_E_ARG, "out of host memory");
+    if (!T) {
+        destroy_impl(h);
+        *out = nullptr;
+        return fail(XFB_E_ARG, "out of host memory");
+    }
     memset(T, 0, sizeof(*T));
     T->nranks = nranks; T->nlocal = 1; T->local[0] = h; T->loopback = false;
     ncclUniqueId id;
@@ -846,6 +850,11 @@ extern "C" int xfb_create_dist(xfb_handle *out, int nx, int ny, float lx, float 
         cudaMemcpyAsync(&flag, flag_d, sizeof(float), cudaMemcpyDeviceToHost, h->comm_stream);
         cudaStreamSynchronize(h->comm_stream);
         h->p2p = flag > 0.5f;
+        if (!h->p2p)                       // some rank could not map its peers: nobody uses the mappings, give them back
+            for (int q = 0; q < nranks; ++q) {
+                if (q != rank && h->peer_recv[q]) cudaIpcCloseMemHandle(h->peer_recv[q]);
+                h->peer_recv[q] = nullptr;
+            }
         // who moves the bytes: copy engines, or a few CTAs of plain loads/stores (XFB_SLAB_PUSH=sm|ce).  The persistent
         // stepper kernels (NX, NY <= 8192) leave no SM free for a concurrent push kernel, so those grids default to ce.
         const char *push = getenv("XFB_SLAB_PUSH");
