@@ -233,7 +233,14 @@ int main(int argc, char *args[])
     auto owner = [&](int m, int *local) { int d = 0; while (m >= first[d] + count[d]) ++d; *local = m - first[d]; return hs[d]; };
     xfb_handle h = hs[0];
 
-    std::vector<float> field(GRIDS), src(GRIDS, 0.0f);
+    std::vector<float> field(GRIDS);
+    // the forcing field of a step is read from the recipe stream straight into page-locked memory: its upload then runs at
+    // the full PCIe rate (a pageable 8192^2 field takes several step times)
+    float *src = nullptr;
+    if (recipe_type != EMPTY) {
+        CHECK(xfb_host_alloc(&src, GRIDS));
+        std::memset(src, 0, sizeof(float) * GRIDS);
+    }
     char filename[1024], pattern[1024];
     VortSrcRecipeReader vs_reader;
     if (vs_reader.init(recipe_type, vort_src_filename, GRIDS) != 0) return 1;
@@ -360,7 +367,7 @@ int main(int argc, char *args[])
             if (!quiet)
                 for (int s = step + 1; s < step + chunk; ++s) std::printf("# Step %d, time = %.2f\n", s, s * dt);
         } else {
-            const int got = vs_reader.read(step * dt, src.data());       // main-shallow-water.cpp:304
+            const int got = vs_reader.read(step * dt, src);       // main-shallow-water.cpp:304
             if (got < 0) {
                 // a short read of the forcing stream: the reference ignores the return value and integrates on with a
                 // half-filled buffer (vorticity_source.cpp:116-126); stopping is the safe reading of that
@@ -371,7 +378,7 @@ int main(int argc, char *args[])
             for (int m = 0; got == 1 && m < members; ++m) {            // the same forcing for every member
                 int lm = 0;
                 xfb_handle hm = owner(m, &lm);
-                if (xfb_set_source(hm, lm, src.data()) != 0) {
+                if (xfb_set_source(hm, lm, src) != 0) {
                     std::fprintf(stderr, "main.out: %s\n", xfb_last_error());
                     shutdown_writer();
                     return 1;
@@ -395,6 +402,7 @@ int main(int argc, char *args[])
         return 1;
     }
     for (float *pb : pinned) xfb_host_free(pb);
+    xfb_host_free(src);
     if (log_fd) std::fclose(log_fd);
     for (xfb_handle hd : hs) xfb_destroy(hd);
     (void)h;
