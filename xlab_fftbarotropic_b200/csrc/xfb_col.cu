@@ -52,7 +52,7 @@ static EncodeTiledFn encode_tiled()
 
 // pair-layout array of `rows` rows x `pitch` complex columns as a 2-D tensor of 8-byte elements:
 // inner dimension 2*pitch (column-major within a row pair: x = 2*j + (i & 1)), outer dimension rows/2
-static int make_pair_map(CUtensorMap *m, const void *base, long long rows, int pitch, int tw, int boxr)
+static int make_pair_map(CUtensorMap *m, const void *base, long long rows, int pitch, int tw, int boxr, bool swizzle32 = false)
 {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return (int)cudaErrorNotSupported;
@@ -61,7 +61,8 @@ static int make_pair_map(CUtensorMap *m, const void *base, long long rows, int p
     cuuint32_t box[2] = {(cuuint32_t)(tw * 2), (cuuint32_t)boxr};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
@@ -77,14 +78,14 @@ static int launch_colt_t(const ColParams &p, int batch, cudaStream_t st)
     ColTMaps maps;
     const long long rows = (long long)NX * batch;
     if (MODE == COL_STEP || MODE == COL_FWDT || MODE == COL_TSTEP) {
-        if (int e = make_pair_map(&maps.jint, p.jint, rows, p.pitch, C::TW, C::BOXR)) return e;
+        if (int e = make_pair_map(&maps.jint, p.jint, rows, p.pitch, C::TW, C::BOXR, C::SWZ)) return e;
     } else {
         maps.jint = CUtensorMap();
     }
     const int nout = (MODE == COL_FWDT) ? 0 : (MODE == COL_DIAG) ? p.nfields : (MODE == COL_TSTEP || MODE == COL_TPRO) ? 2 : 4;
     for (int f = 0; f < 4; ++f) {
         if (f < nout) {
-            if (int e = make_pair_map(&maps.t[f], p.t_out[f], rows, p.pitch, C::TW, C::BOXR)) return e;
+            if (int e = make_pair_map(&maps.t[f], p.t_out[f], rows, p.pitch, C::TW, C::BOXR, C::SWZ)) return e;
         } else {
             maps.t[f] = (f > 0 && nout > 0) ? maps.t[0] : CUtensorMap();
         }

@@ -24,6 +24,11 @@
 
 #include "xfb_col.cuh"
 
+// XFB_COLT_SWZ=0 at compile time builds the unswizzled tile staging (A/B: tools/ab_lib.py with XFB_LIB)
+#ifndef XFB_COLT_SWZ
+#define XFB_COLT_SWZ 1
+#endif
+
 namespace xfb {
 
 template <int NX>
@@ -50,6 +55,12 @@ struct ColTCfg {
 #else
     static constexpr bool RING = false;
 #endif
+    // FW == 1 with two-column tiles (8192): a warp's 8-byte accesses to a staged tile touch 16 of every 32 bytes -- row pair
+    // p and row pair p + 4 share their shared-memory banks (2-way conflicts on every tile store and ring read, 8.4 M
+    // extra wavefronts per launch).  The tiles are therefore staged with the TMA engine's 32-byte swizzle (address bit 4
+    // ^= bit 7: the two 16-byte column chunks of a row pair trade places in every other group of four row pairs) and the
+    // threads apply the same exchange to their column index: conflict-free, no extra instruction in the loops.
+    static constexpr bool SWZ = (XFB_COLT_SWZ != 0) && (TW == 2) && (FW == 1);
     static constexpr int RING_SLOTS = 3;
     static constexpr int BOX_BYTES = BOXR * TW * 2 * (int)sizeof(cpx);
     static constexpr int SMEM = (SPLIT_IN ? 2 : 1) * S_BYTES + F_BYTES + (RING ? RING_SLOTS * BOX_BYTES : 0) + 1024;   // + alignment slack
@@ -83,6 +94,7 @@ struct ColtRing {
     cpx *ring;
     unsigned long long *bar;
     int s_off;            // this thread's element of a box: ((t >> 1) * TW) * 2 + (t & 1), + 2 * column
+    int c0_off;           // 2 * (shared-memory chunk of column 0): 0, or 2 where the 32-byte swizzle exchanges the columns
     unsigned tin;         // this thread's incoming TMEM region: + cg * 32 + 2 * q
     int cx, cy;           // TMA coordinates of box 0 of the tile being streamed in
     int q;                // next box of that tile to consume; >= 16: nothing to do
@@ -111,7 +123,7 @@ struct ColtRing {
         if (threadIdx.x == 0 && q + 2 < 16) issue(q + 2, slot == 0 ? 2 : slot - 1);      // (slot + 2) mod 3
         mbar_wait(bar + slot, parity);
         const cpx *src = ring + (size_t)slot * BOX_ELEMS + s_off;
-        const cpx a = src[0], b = src[2];
+        const cpx a = src[c0_off], b = src[2 - c0_off];
         tmem_park1(tin + (unsigned)(2 * q), a);
         tmem_park1(tin + (unsigned)(32 + 2 * q), b);
         ++q;
@@ -179,7 +191,9 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
 
     // element (row i = t + k*G, tile column col) of S: ((i >> 1) * TW + col) * 2 + (i & 1); k-stride = G * TW
     const int s_base = ((t[0] >> 1) * TW) * 2 + (t[0] & 1);
-    if (TRING) rs.s_off = s_base;
+    // 32-byte swizzle of the staged tiles (ColTCfg::SWZ): byte address bit 7 = bit 3 of the row
+    const int swz = C::SWZ ? ((t[0] >> 3) & 1) : 0;
+    if (TRING) { rs.s_off = s_base; rs.c0_off = 2 * swz; }
 
     constexpr bool HAS_FWD = (MODE == COL_STEP || MODE == COL_FWDT);
     constexpr bool PIPE_TAIL = (MODE == COL_STEP) && !C::SPLIT_IN && (C::NBOX > 1) && (C::NBOX <= 16) && !TRING;
@@ -234,7 +248,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
                 if (TRING) {
                     tmem_unpark(rs.tin + (unsigned)(cg * 32), v[0]);       // this tile was parked while the previous one ran
                 } else {
-                    const cpx *src = SI + s_base + 2 * col;
+                    const cpx *src = SI + s_base + 2 * (col ^ swz);
 #pragma unroll
                     for (int k = 0; k < 16; ++k) v[0][k] = src[k * G * TW];
                 }
@@ -425,7 +439,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
                 // Thread 0 waits inside the transform, before its last exchange barrier (col_fft, drain_tma).
                 if (TRING) col_fft<NX, FW, 1, ColtRing<NX>>(v, F, t, c, tw, cg == 0, rs);
                 else col_fft<NX, FW, 1>(v, F, t, c, tw, cg == 0);
-                cpx *dst = S + s_base + 2 * col;
+                cpx *dst = S + s_base + 2 * (col ^ swz);
 #pragma unroll
                 for (int k = 0; k < 16; ++k) dst[k * G * TW] = cswap(v[0][k]);
             }
