@@ -216,9 +216,25 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
             tma_load_2d(SI + (size_t)b * C::BOXR * TW * 2, &maps.jint, tl * TW * 2, member * (NX / 2) + b * C::BOXR, &full);
     }
 
+    // ky of this thread's column in each column group of a tile, loaded a tile ahead: a __ldg right in front of its first
+    // use -- behind the asm volatile statements of the tensor-memory traffic the compiler cannot hoist it over -- left its
+    // whole L2 latency exposed with all warps waiting at the same point, ten times per tile at 8192 (4.4 % of the
+    // kernel's stall samples on the first one alone, profiles/r02c_8192_*)
+    float ky_n0 = 0.f, ky_n1 = 0.f;
+    if (tile < tiles_total) {
+        const int jn = p.j_base + (tile % tiles_per_member) * TW + c[0];
+        ky_n0 = __ldg(p.ky + jn);
+        if (NG > 1) ky_n1 = __ldg(p.ky + jn + FW);
+    }
     for (; tile < tiles_total; tile += gridDim.x) {
         const int member = tile / tiles_per_member, tl = tile - member * tiles_per_member;
         const int j0 = tl * TW;
+        const float ky_t0 = ky_n0, ky_t1 = ky_n1;
+        if (tile + (int)gridDim.x < tiles_total) {
+            const int jn = p.j_base + ((tile + (int)gridDim.x) % tiles_per_member) * TW + c[0];
+            ky_n0 = __ldg(p.ky + jn);
+            if (NG > 1) ky_n1 = __ldg(p.ky + jn + FW);
+        }
         const size_t moff = (size_t)member * (size_t)p.member_stride;
         const int tmy = member * (NX / 2), tmx = tl * TW * 2;      // TMA coordinates of this tile
         cpx v[1][16];
@@ -253,7 +269,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
                     for (int k = 0; k < 16; ++k) v[0][k] = src[k * G * TW];
                 }
                 const int j = p.j_base + j0 + col;
-                const float kyv = __ldg(p.ky + j);
+                const float kyv = (NG == 1 || cg == 0) ? ky_t0 : ky_t1;
                 const float ky2 = kyv * kyv;
                 const size_t soff = moff + (size_t)(tl * NG + cg) * (size_t)p.st_tile_stride;
                 const size_t e0 = soff + (size_t)t[0] * srow + c[0];
@@ -382,7 +398,7 @@ colt_kernel(const ColParams p, const __grid_constant__ ColTMaps maps, const int 
             for (int cg = 0; cg < NG; ++cg) {
                 const int col = cg * FW + c[0];
                 const int j = p.j_base + j0 + col;
-                const float ky = __ldg(p.ky + j);
+                const float ky = (NG == 1 || cg == 0) ? ky_t0 : ky_t1;
                 const float ky2 = ky * ky;
                 if (TKEEP) {
                     tmem_unpark(tpark + (unsigned)(cg * 32), v[0]);
