@@ -298,8 +298,8 @@ int generic_inv2d(xfb_handle h, const cpx *spec_in, cpx *tmp, float *real_out, f
     return 0;
 }
 
-// nsteps RK4 steps, one kernel per loop of src/main.cpp:286-317
-int generic_step(xfb_handle h, int nsteps, float dt)
+// one RK4 step of every member, one kernel per loop of src/main.cpp:286-317
+static int generic_one_step(xfb_handle h, float dt)
 {
     const int P = h->hy;
     const long long n = (long long)h->grids, hn = (long long)h->nx * h->hy;
@@ -310,31 +310,71 @@ int generic_step(xfb_handle h, int nsteps, float dt)
         const float *src = h->has_src ? h->src + (size_t)m * h->grids : nullptr;
         float *fa = h->real_a, *fb = h->real_b, *fc = h->real_c, *fd = (float *)h->t[0];      // dvortdx, dvortdy, -u, v
         cpx *tmp = h->spec_a, *tmp2 = h->spec_b, *psi = h->t[1], *T = h->jint;
-        for (int s = 0; s < nsteps; ++s)
-            for (int k = 1; k <= 4; ++k) {
-                const cpx *z = (k == 1) ? z0 : zk;
-                if (launch_pw(h, OP_GRADX, z, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fa, scale, 0)) return XFB_E_CUDA;       // :151-154
-                if (launch_pw(h, OP_GRADY, z, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fb, scale, 0)) return XFB_E_CUDA;       // :165-168
-                if (launch_pw(h, OP_INVLAP, z, P, psi, P, P)) return XFB_E_CUDA;                                                    // :179
-                if (launch_pw(h, OP_GRADY, psi, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fc, scale, 1)) return XFB_E_CUDA;     // :198-201
-                if (launch_pw(h, OP_GRADX, psi, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fd, scale, 0)) return XFB_E_CUDA;     // :212-214
-                GLAUNCH(h, (gen_jacobian<<<gb, 256, 0, h->stream>>>(fc, fa, fd, fb, src, fa, n)));                                  // :225-227
-                if (generic_fwd2d(h, fa, tmp2, T)) return XFB_E_CUDA;                                                                // :237
-                GLAUNCH(h, (gen_stage<<<hb, 256, 0, h->stream>>>(T, z0, zk, acc, h->nx, h->hy, h->kx2, h->ky2, h->mask_kd, h->nu, dt,
-                                                                  (k == 3) ? dt : dt / 2.0f, k)));
-                if (h->has_tracer) {
-                    // passive tracer (xfb_set_tracer): the same loops with c for vort and kappa for NU; -u, v of this
-                    // stage are still in fc, fd
-                    cpx *c0 = h->c0 + (size_t)m * h->hpad, *ck = h->ck + (size_t)m * h->hpad, *cacc = h->cacc + (size_t)m * h->hpad;
-                    const cpx *c = (k == 1) ? c0 : ck;
-                    if (launch_pw(h, OP_GRADX, c, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fa, scale, 0)) return XFB_E_CUDA;
-                    if (launch_pw(h, OP_GRADY, c, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fb, scale, 0)) return XFB_E_CUDA;
-                    GLAUNCH(h, (gen_jacobian<<<gb, 256, 0, h->stream>>>(fc, fa, fd, fb, nullptr, fa, n)));
-                    if (generic_fwd2d(h, fa, tmp2, h->cjint)) return XFB_E_CUDA;
-                    GLAUNCH(h, (gen_stage<<<hb, 256, 0, h->stream>>>(h->cjint, c0, ck, cacc, h->nx, h->hy, h->kx2, h->ky2, h->mask_kd,
-                                                                      h->kappa, dt, (k == 3) ? dt : dt / 2.0f, k)));
-                }
+        for (int k = 1; k <= 4; ++k) {
+            const cpx *z = (k == 1) ? z0 : zk;
+            if (launch_pw(h, OP_GRADX, z, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fa, scale, 0)) return XFB_E_CUDA;       // :151-154
+            if (launch_pw(h, OP_GRADY, z, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fb, scale, 0)) return XFB_E_CUDA;       // :165-168
+            if (launch_pw(h, OP_INVLAP, z, P, psi, P, P)) return XFB_E_CUDA;                                                    // :179
+            if (launch_pw(h, OP_GRADY, psi, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fc, scale, 1)) return XFB_E_CUDA;     // :198-201
+            if (launch_pw(h, OP_GRADX, psi, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fd, scale, 0)) return XFB_E_CUDA;     // :212-214
+            GLAUNCH(h, (gen_jacobian<<<gb, 256, 0, h->stream>>>(fc, fa, fd, fb, src, fa, n)));                                  // :225-227
+            if (generic_fwd2d(h, fa, tmp2, T)) return XFB_E_CUDA;                                                                // :237
+            GLAUNCH(h, (gen_stage<<<hb, 256, 0, h->stream>>>(T, z0, zk, acc, h->nx, h->hy, h->kx2, h->ky2, h->mask_kd, h->nu, dt,
+                                                              (k == 3) ? dt : dt / 2.0f, k)));
+            if (h->has_tracer) {
+                // passive tracer (xfb_set_tracer): the same loops with c for vort and kappa for NU; -u, v of this
+                // stage are still in fc, fd
+                cpx *c0 = h->c0 + (size_t)m * h->hpad, *ck = h->ck + (size_t)m * h->hpad, *cacc = h->cacc + (size_t)m * h->hpad;
+                const cpx *c = (k == 1) ? c0 : ck;
+                if (launch_pw(h, OP_GRADX, c, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fa, scale, 0)) return XFB_E_CUDA;
+                if (launch_pw(h, OP_GRADY, c, P, tmp, P, P) || generic_inv2d(h, tmp, tmp2, fb, scale, 0)) return XFB_E_CUDA;
+                GLAUNCH(h, (gen_jacobian<<<gb, 256, 0, h->stream>>>(fc, fa, fd, fb, nullptr, fa, n)));
+                if (generic_fwd2d(h, fa, tmp2, h->cjint)) return XFB_E_CUDA;
+                GLAUNCH(h, (gen_stage<<<hb, 256, 0, h->stream>>>(h->cjint, c0, ck, cacc, h->nx, h->hy, h->kx2, h->ky2, h->mask_kd,
+                                                                  h->kappa, dt, (k == 3) ? dt : dt / 2.0f, k)));
             }
+        }
+    }
+    return 0;
+}
+
+// nsteps RK4 steps.  A step is 72 short launches per member (124 with the tracer) on grids that live in L2 -- launch
+// gaps, not kernels, bound it --, so like the fused stepper (xfb_step) the step is captured once into a CUDA graph and
+// replayed; the first step of a handle runs eagerly, XFB_NO_GRAPH=1 keeps the eager path.  The graph bakes in dt, the
+// source pointer and the tracer's state (xfb_set_tracer drops it).
+int generic_step(xfb_handle h, int nsteps, float dt)
+{
+    static const bool no_graph = getenv("XFB_NO_GRAPH") && atoi(getenv("XFB_NO_GRAPH")) != 0;
+    int s = 0;
+    if (nsteps > 0 && (!h->warmed || no_graph)) {
+        const int eager = no_graph ? nsteps : 1;
+        for (; s < eager; ++s)
+            if (int e = generic_one_step(h, dt)) return e;
+        h->warmed = true;
+    }
+    if (s < nsteps) {
+        const void *src_now = h->has_src ? (const void *)h->src : nullptr;
+        if (!h->step_graph || h->graph_dt != dt || h->graph_src != src_now) {
+            if (h->step_graph) { cudaGraphExecDestroy((cudaGraphExec_t)h->step_graph); h->step_graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+            const long long l0 = h->launches;
+            const int e = generic_one_step(h, dt);
+            const int per_step = (int)(h->launches - l0);
+            h->launches = l0;
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+            if (e) { if (g) cudaGraphDestroy(g); return e; }
+            if (ce != cudaSuccess) return fail(XFB_E_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+            cudaGraphExec_t ge = nullptr;
+            ce = cudaGraphInstantiate(&ge, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) return fail(XFB_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+            h->step_graph = ge; h->graph_dt = dt; h->graph_src = src_now; h->graph_launches = per_step;
+        }
+        for (; s < nsteps; ++s) {
+            CK(cudaGraphLaunch((cudaGraphExec_t)h->step_graph, h->stream));
+            h->launches += h->graph_launches;
+        }
     }
     return 0;
 }

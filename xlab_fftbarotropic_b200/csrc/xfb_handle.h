@@ -65,6 +65,7 @@ struct xfb_handle_s {
     void *step_graph;    // cudaGraphExec_t of one RK4 step (8 launches), valid for graph_dt / graph_src
     float graph_dt;
     const void *graph_src;
+    int graph_launches;  // launches one replay of step_graph stands for (generic path; the fused step has 8 or 16)
     // passive tracer (xfb_set_tracer), allocated on first use: state like z0/zk/acc/jint, two gradient product arrays
     xfb::cpx *c0, *ck, *cacc, *cjint, *tc[2];
     float kappa;
